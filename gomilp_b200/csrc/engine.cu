@@ -1,0 +1,421 @@
+// engine.cu — C ABI of libgomilp_b200.so (include/gomilp_b200.h): device management, host<->device
+// staging, tier selection and launch of the simplex wave kernel. No CPU fallback anywhere: every
+// compute entry point returns GM_ERR_NO_DEVICE when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gomilp_b200.h"
+#include "simplex_cta.cuh"
+
+namespace {
+
+constexpr int kSmemThreads = 256;  // tier 1: one LP per CTA, everything in shared memory
+constexpr int kHbmThreads = 512;   // tier 2/3: W and Bi in HBM
+
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) simplex_wave_smem(gm::BatchParams P) {
+    extern __shared__ double smem[];
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
+    gm::cta_main(P, smem, smem + w.big_doubles, &slot);
+}
+
+// big part (W, Bi) in HBM, small part in shared memory
+template <int T>
+__global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
+    extern __shared__ double smem[];
+    __shared__ int slot;
+    gm::cta_main(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, &slot);
+}
+
+// everything in HBM (very large m + n)
+template <int T>
+__global__ void __launch_bounds__(T, 1) simplex_wave_hbm_all(gm::BatchParams P) {
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
+    double* base = P.work + (size_t)blockIdx.x * P.work_stride;
+    gm::cta_main(P, base, base + w.big_doubles, &slot);
+}
+
+struct Root {
+    double *c = nullptr, *A = nullptr, *b = nullptr;
+    int m0 = 0, n0 = 0;
+};
+
+struct Engine {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    int sms = 0;
+    size_t smem_optin = 0;
+    gm_options opt{0, 0, 0, 0};
+    std::map<gm_root_t, Root> roots;
+    gm_root_t next_root = 1;
+};
+Engine g;
+
+thread_local std::string t_err;
+thread_local gm_timing t_timing{};
+
+int fail(cudaError_t e, const char* what) {
+    t_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return GM_ERR_CUDA;
+}
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) return fail(e_, #call); \
+    } while (0)
+
+int ensure_ready() {
+    if (g.ready) {
+        cudaSetDevice(g.device);  // bind the calling (possibly new) host thread
+        return GM_OK;
+    }
+    return gm_init(0);
+}
+
+}  // namespace
+
+namespace gm_internal {
+
+// Launches the wave kernel over `P.count` LPs whose problem/outputs are already device-resident.
+// Fills work/queue fields of P. Asynchronous on `stream`; kernel time is recorded into ev0/ev1 if given.
+int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, gm_timing* tm) {
+    const int m = P.m0 + P.L, n = P.n0 + P.L;
+    if (P.count <= 0) return GM_OK;
+    if (m <= 0 || n <= 0) return GM_ERR_BAD_SHAPE;
+    P.max_pivots = g.opt.max_pivots;
+    P.refactor_period = g.opt.refactor_period;
+    const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads);
+    const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads);
+    const size_t smem_all = w1.big_bytes + w1.small_bytes;
+    int tier = g.opt.force_tier;
+    if (tier == 0) tier = smem_all + 64 <= g.smem_optin ? 1 : (w2.small_bytes + 64 <= g.smem_optin ? 2 : 3);
+    if (tier == 1 && smem_all + 64 > g.smem_optin) return GM_ERR_TOO_LARGE;
+    if (tier == 2 && w2.small_bytes + 64 > g.smem_optin) return GM_ERR_TOO_LARGE;
+
+    int* queue = nullptr;
+    CK(cudaMallocAsync(&queue, sizeof(int), stream));
+    CK(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+    P.queue = queue;
+    double* work = nullptr;
+    int grid = 0, block = 0;
+    size_t smem = 0;
+    if (tier == 1) {
+        block = kSmemThreads;
+        smem = smem_all;
+        int per_sm = 0;
+        // two kernels: up to 2 CTAs/SM (register cap 128) or many small ones
+        auto kern = simplex_wave_smem<kSmemThreads, 2>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = (int)std::min<long long>(P.count, (long long)g.sms * per_sm);
+        if (ev0) CK(cudaEventRecord(ev0, stream));
+        kern<<<grid, block, smem, stream>>>(P);
+    } else {
+        block = kHbmThreads;
+        const size_t per_cta = tier == 2 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8);
+        grid = (int)std::min<long long>(P.count, (long long)g.sms);
+        CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));
+        P.work = work;
+        P.work_stride = (long long)per_cta;
+        if (tier == 2) {
+            smem = w2.small_bytes;
+            auto kern = simplex_wave_hbm<kHbmThreads>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (ev0) CK(cudaEventRecord(ev0, stream));
+            kern<<<grid, block, smem, stream>>>(P);
+        } else {
+            auto kern = simplex_wave_hbm_all<kHbmThreads>;
+            if (ev0) CK(cudaEventRecord(ev0, stream));
+            kern<<<grid, block, 0, stream>>>(P);
+        }
+    }
+    CK(cudaGetLastError());
+    if (ev1) CK(cudaEventRecord(ev1, stream));
+    if (work) CK(cudaFreeAsync(work, stream));
+    CK(cudaFreeAsync(queue, stream));
+    if (tm) {
+        tm->tier = tier;
+        tm->grid = grid;
+        tm->block = block;
+        tm->smem_bytes = (int64_t)smem;
+        tm->launches += 1;
+        tm->lps += P.count;
+    }
+    return GM_OK;
+}
+
+int root_lookup(gm_root_t h, const double** c, const double** A, const double** b, int* m0, int* n0) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    auto it = g.roots.find(h);
+    if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
+    *c = it->second.c; *A = it->second.A; *b = it->second.b;
+    *m0 = it->second.m0; *n0 = it->second.n0;
+    return GM_OK;
+}
+
+}  // namespace gm_internal
+
+using gm_internal::launch_wave;
+
+extern "C" {
+
+int gm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* gm_last_error(void) { return t_err.c_str(); }
+
+int gm_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        t_err = "no CUDA device (the engine has no CPU fallback)";
+        return GM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return GM_ERR_BAD_ARGUMENT;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g.device = device;
+    g.sms = prop.multiProcessorCount;
+    g.smem_optin = prop.sharedMemPerBlockOptin;
+    g.ready = true;
+    return GM_OK;
+}
+
+int gm_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.ready) return GM_OK;
+    for (auto& kv : g.roots) {
+        cudaFree(kv.second.c);
+        cudaFree(kv.second.A);
+        cudaFree(kv.second.b);
+    }
+    g.roots.clear();
+    g.ready = false;
+    return GM_OK;
+}
+
+int gm_set_options(const gm_options* opt) {
+    if (!opt) return GM_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.opt = *opt;
+    return GM_OK;
+}
+
+int gm_last_timing(gm_timing* out) {
+    if (!out) return GM_ERR_BAD_ARGUMENT;
+    *out = t_timing;
+    return GM_OK;
+}
+
+int gm_simplex_batch_device(int64_t count, const double* d_c, const double* d_A, const double* d_b, int64_t m,
+                            int64_t n, double tol, int32_t* d_status, double* d_optF, double* d_optX,
+                            int64_t* d_basis, int32_t* d_stats, void* stream) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (count < 0 || m <= 0 || n <= 0 || count > INT32_MAX || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;
+    if (!d_c || !d_A || !d_b || !d_status || !d_optF || !d_optX) return GM_ERR_BAD_ARGUMENT;
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c = d_c; P.A = d_A; P.b = d_b;
+    P.c_stride = n; P.A_stride = m * n; P.b_stride = m;
+    P.lda = (int)n; P.m0 = (int)m; P.n0 = (int)n; P.L = 0;
+    P.tol = tol; P.count = (int)count;
+    P.status = d_status; P.optF = d_optF; P.x = d_optX; P.x_stride = n; P.x_len = (int)n;
+    P.basis = reinterpret_cast<long long*>(d_basis); P.stats = d_stats;
+    t_timing = gm_timing{};
+    return launch_wave(P, (cudaStream_t)stream, nullptr, nullptr, &t_timing);
+}
+
+}  // extern "C"
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit DevBuf(cudaStream_t s_) : s(s_) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+struct StreamEvents {
+    cudaStream_t s = nullptr;
+    cudaEvent_t e[6] = {};
+    cudaError_t init() {
+        cudaError_t r = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        for (int i = 0; i < 6 && r == cudaSuccess; ++i) r = cudaEventCreate(&e[i]);
+        return r;
+    }
+    ~StreamEvents() {
+        for (auto& ev : e) if (ev) cudaEventDestroy(ev);
+        if (s) cudaStreamDestroy(s);
+    }
+};
+float ms(cudaEvent_t a, cudaEvent_t b) {
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    return t;
+}
+}  // namespace
+
+// shared body of the host-buffer entry points: per-LP roots (stride != 0) or wave over a device root
+static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A, int64_t h_lda, const double* h_b,
+                         const int64_t* h_ib, const int32_t* h_bvar, const double* h_bsign, const double* h_brhs,
+                         int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats) {
+    StreamEvents se;
+    CK(se.init());
+    cudaStream_t st = se.s;
+    const int64_t count = P.count, m0 = P.m0, n0 = P.n0, L = P.L, m = m0 + L;
+    DevBuf dc(st), dA(st), db(st), dib(st), dbv(st), dbs(st), dbr(st), dst(st), dF(st), dX(st), dB(st), dS(st);
+    CK(cudaEventRecord(se.e[0], st));
+    if (h_A) {  // per-LP roots travel with the call
+        CK(dc.alloc(sizeof(double) * count * n0));
+        CK(dA.alloc(sizeof(double) * count * m0 * n0));
+        CK(db.alloc(sizeof(double) * count * m0));
+        CK(cudaMemcpyAsync(dc.p, h_c, sizeof(double) * count * n0, cudaMemcpyHostToDevice, st));
+        if (h_lda == n0) {
+            CK(cudaMemcpyAsync(dA.p, h_A, sizeof(double) * count * m0 * n0, cudaMemcpyHostToDevice, st));
+        } else {  // strided single matrix (gm_simplex with lda > n)
+            CK(cudaMemcpy2DAsync(dA.p, sizeof(double) * n0, h_A, sizeof(double) * h_lda, sizeof(double) * n0,
+                                 count * m0, cudaMemcpyHostToDevice, st));
+        }
+        CK(cudaMemcpyAsync(db.p, h_b, sizeof(double) * count * m0, cudaMemcpyHostToDevice, st));
+        P.c = dc.as<double>(); P.A = dA.as<double>(); P.b = db.as<double>();
+        P.lda = (int)n0;
+    }
+    if (h_ib) {
+        CK(dib.alloc(sizeof(int64_t) * count * m));
+        CK(cudaMemcpyAsync(dib.p, h_ib, sizeof(int64_t) * count * m, cudaMemcpyHostToDevice, st));
+        P.initial_basic = dib.as<long long>();
+    }
+    if (L > 0) {
+        CK(dbv.alloc(sizeof(int32_t) * count * L));
+        CK(dbs.alloc(sizeof(double) * count * L));
+        CK(dbr.alloc(sizeof(double) * count * L));
+        CK(cudaMemcpyAsync(dbv.p, h_bvar, sizeof(int32_t) * count * L, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dbs.p, h_bsign, sizeof(double) * count * L, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dbr.p, h_brhs, sizeof(double) * count * L, cudaMemcpyHostToDevice, st));
+        P.bvar = dbv.as<int>(); P.bsign = dbs.as<double>(); P.brhs = dbr.as<double>();
+    }
+    CK(dst.alloc(sizeof(int32_t) * count));
+    CK(dF.alloc(sizeof(double) * count));
+    CK(dX.alloc(sizeof(double) * count * P.x_len));
+    P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.x_stride = P.x_len;
+    if (basis) { CK(dB.alloc(sizeof(int64_t) * count * m)); P.basis = dB.as<long long>(); }
+    if (stats) { CK(dS.alloc(sizeof(int32_t) * count * 8)); P.stats = dS.as<int>(); }
+    t_timing = gm_timing{};
+    int rc = launch_wave(P, st, se.e[1], se.e[2], &t_timing);
+    if (rc != GM_OK) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(optF, dF.p, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(optX, dX.p, sizeof(double) * count * P.x_len, cudaMemcpyDeviceToHost, st));
+    if (basis) CK(cudaMemcpyAsync(basis, dB.p, sizeof(int64_t) * count * m, cudaMemcpyDeviceToHost, st));
+    if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * count * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(se.e[3], st));
+    CK(cudaStreamSynchronize(st));
+    t_timing.h2d_ms = ms(se.e[0], se.e[1]);
+    t_timing.kernel_ms = ms(se.e[1], se.e[2]);
+    t_timing.d2h_ms = ms(se.e[2], se.e[3]);
+    return GM_OK;
+}
+
+extern "C" {
+
+int gm_simplex_batch(int64_t count, const double* c, const double* A, const double* b, int64_t m, int64_t n,
+                     double tol, int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (count < 0 || m <= 0 || n <= 0 || count > INT32_MAX || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;
+    if (count == 0) return GM_OK;
+    if (!c || !A || !b || !status || !optF || !optX) return GM_ERR_BAD_ARGUMENT;
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c_stride = n; P.A_stride = m * n; P.b_stride = m;
+    P.m0 = (int)m; P.n0 = (int)n; P.L = 0; P.tol = tol; P.count = (int)count; P.x_len = (int)n;
+    return run_host_call(P, c, A, n, b, nullptr, nullptr, nullptr, nullptr, status, optF, optX, basis, stats);
+}
+
+int gm_simplex(const double* c, const double* A, int64_t lda, const double* b, int64_t m, int64_t n, double tol,
+               const int64_t* initialBasic, double* optF, double* optX, int64_t* basisOut, int64_t* pivots) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (m <= 0 || n <= 0 || lda < n || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;  // simplex.go:387-398 panics
+    if (!c || !A || !b || !optF || !optX) return GM_ERR_BAD_ARGUMENT;
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c_stride = n; P.A_stride = m * n; P.b_stride = m;
+    P.m0 = (int)m; P.n0 = (int)n; P.L = 0; P.tol = tol; P.count = 1; P.x_len = (int)n;
+    int32_t status = GM_ERR_CUDA;
+    int32_t stats[8] = {0};
+    rc = run_host_call(P, c, A, lda, b, initialBasic, nullptr, nullptr, nullptr, &status, optF, optX, basisOut, stats);
+    if (rc != GM_OK) return rc;
+    if (pivots) *pivots = (int64_t)stats[0] + stats[1];
+    return status;
+}
+
+int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
+                   gm_root_t* out) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (m0 <= 0 || n0 <= 0 || lda < n0) return GM_ERR_BAD_SHAPE;
+    if (!c0 || !A0 || !b0 || !out) return GM_ERR_BAD_ARGUMENT;
+    Root r;
+    r.m0 = (int)m0; r.n0 = (int)n0;
+    CK(cudaMalloc(&r.c, sizeof(double) * n0));
+    CK(cudaMalloc(&r.A, sizeof(double) * m0 * n0));
+    CK(cudaMalloc(&r.b, sizeof(double) * m0));
+    CK(cudaMemcpy(r.c, c0, sizeof(double) * n0, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(r.A, sizeof(double) * n0, A0, sizeof(double) * lda, sizeof(double) * n0, m0, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(r.b, b0, sizeof(double) * m0, cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> lk(g.mu);
+    *out = g.next_root++;
+    g.roots[*out] = r;
+    return GM_OK;
+}
+
+int gm_free_root(gm_root_t root) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    auto it = g.roots.find(root);
+    if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
+    cudaFree(it->second.c);
+    cudaFree(it->second.A);
+    cudaFree(it->second.b);
+    g.roots.erase(it);
+    return GM_OK;
+}
+
+int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                  const double* brhs, int32_t* status, double* z, double* x, int64_t* basis, int32_t* stats) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (nodes < 0 || L < 0 || nodes > INT32_MAX) return GM_ERR_BAD_SHAPE;
+    if (nodes == 0) return GM_OK;
+    if (!status || !z || !x || (L > 0 && (!bvar || !bsign || !brhs))) return GM_ERR_BAD_ARGUMENT;
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    int m0, n0;
+    rc = gm_internal::root_lookup(root, &P.c, &P.A, &P.b, &m0, &n0);
+    if (rc != GM_OK) return rc;
+    for (int64_t i = 0; i < nodes * L; ++i)
+        if (bvar[i] < 0 || bvar[i] >= n0) return GM_ERR_BAD_ARGUMENT;
+    P.m0 = m0; P.n0 = n0; P.lda = n0; P.L = (int)L; P.tol = 0.0;  // subproblem.go:154,172 pass tol = 0
+    P.count = (int)nodes; P.x_len = n0;
+    return run_host_call(P, nullptr, nullptr, 0, nullptr, nullptr, bvar, bsign, brhs, status, z, x, basis, stats);
+}
+
+}  // extern "C"

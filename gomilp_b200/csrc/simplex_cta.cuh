@@ -1,0 +1,934 @@
+// simplex_cta.cuh — one-CTA-per-LP dense two-phase revised simplex (the "wave" kernel).
+//
+// Replaces, for a whole batch / frontier wave at once, the reference's per-node call chain
+//   subProblem.solve            /root/reference/subproblem.go:141-187
+//     combineInequalities       subproblem.go:55-78      (branch rows synthesised on the fly, never stored)
+//     convertToEqualities       subproblem.go:81-139     ([A0 0; G I] read through src_a(), never materialised)
+//     lp.Simplex                vendor/gonum.org/v1/gonum/optimize/convex/lp/simplex.go:88-302
+//       verifyInputs :385-439, findInitialBasic :492-607, findLinearlyIndependent :611-637,
+//       computeMove :306-342, replaceBland :347-383, initializeFromBasic :447-471
+// The DECISIONS are Gonum's: Dantzig pricing with floats.MinIdx first-position ties over the
+// positional non-basic list that is mutated by swaps (simplex.go:174-184,280), ratio test by MinIdx
+// over positions, Bland fallback when the step is <= 0, every tolerance of simplex.go:42-58, Phase I
+// with one artificial column and tol 1e-10, the artificial-still-basic repair scan.
+// The ARITHMETIC is not Gonum's: instead of three fresh LU factorisations per pivot the basis inverse
+// is kept explicitly (m x m, row-major) and updated by a rank-1 (product-form) step; it is rebuilt by
+// Gauss-Jordan inversion with partial pivoting every `refactor_period` pivots and once more before an
+// optimal basis is reported ("polish"), so the returned x comes from fresh factors like Gonum's.
+//
+// Data layout per LP (shared memory when it fits, else a per-CTA slice of an HBM workspace):
+//   W   m x ldw   working copy of [A | artificial] with COLUMNS PERMUTED: columns 0..m-1 are the basic
+//                 columns in basis-position order, columns m.. are the non-basic ones in list-position
+//                 order; a pivot swaps two columns. Row-major with odd ldw: pricing (thread per
+//                 column) and column extraction (thread per row) are both bank-conflict free.
+//   Bi  m x ldb   basis inverse, row-major, odd ldb.
+//   vectors       xb, cb, y (duals), al (B^-1 a_e), mv (ratios), bv (rhs), prow, art, t1, t2, cn, r.
+// All reductions that pick an index return the FIRST minimum (value, position) like floats.MinIdx.
+#pragma once
+#include <math.h>
+#include <limits.h>
+
+#include "../../include/gomilp_status.h"
+#include "cta_rt.cuh"
+
+namespace gm {
+
+struct BatchParams {
+    // ---- problem source (device pointers) -------------------------------------------------------
+    const double* c;  // [count][n0] or one shared root
+    const double* A;  // [count][m0][lda] row-major (Gonum mat.Dense layout) or one shared root
+    const double* b;  // [count][m0]
+    long long c_stride, A_stride, b_stride;  // doubles between consecutive LPs; 0 = shared root
+    int lda;
+    int m0, n0;  // root shape
+    int L;       // branch rows appended per node (wave mode); 0 for plain batches
+    const int* bvar;      // [count][L] variable of each bnbConstraint (subproblem.go:36-44)
+    const double* bsign;  // [count][L] gsharp[var] = +1 / -1
+    const double* brhs;   // [count][L] hsharp
+    const long long* initial_basic;  // [count][m] or nullptr (simplex.go:147-160)
+    double tol;
+    int count;
+    int max_pivots;       // safety cap (the reference has none); <=0: 50*(m+n)+1000
+    int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100
+    // ---- outputs --------------------------------------------------------------------------------
+    int* status;        // [count] gm_status
+    double* optF;       // [count]
+    double* x;          // [count][x_stride], first x_len entries written (n, or n0 in wave mode)
+    long long x_stride;
+    int x_len;
+    long long* basis;  // [count][m] or nullptr; -1 when the reference returns nil
+    int* stats;        // [count][8] or nullptr: pivots phase I, phase II, bland calls, inversions,
+                       //   used phase I, basis-scan fallback used, repair trials, x non-nil
+    // ---- work -----------------------------------------------------------------------------------
+    double* work;           // HBM workspace for the tiers that need one: [gridDim][work_stride]
+    long long work_stride;  // doubles per CTA
+    int* queue;             // work-queue counter (zeroed before launch)
+};
+
+// Workspace of one CTA, split in a "big" part (W and Bi: O(mn) doubles) and a "small" part (vectors,
+// index lists, reduction scratch: O(m+n)). Tier 1 keeps both in shared memory, tier 2 keeps the big
+// part in HBM and the small part in shared memory, tier 3 keeps both in HBM.
+struct WsLayout {
+    int ldw, ldb, nn1;
+    size_t W, Bi;         // offsets in doubles inside the big part
+    size_t big_doubles;
+    size_t xb, cb, y, al, mv, bv, prow, art, t1, t2, cn, r, red;  // offsets in doubles inside the small part
+    size_t small_doubles;
+    size_t basic, nonbasic, inb, redi, ipiv;  // offsets in ints, after the small doubles
+    size_t n_ints;
+    size_t big_bytes, small_bytes;
+};
+
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline WsLayout ws_layout(int m, int n, int T) {
+    WsLayout w;
+    w.ldw = (n + 1) | 1;
+    w.ldb = m | 1;
+    w.nn1 = (n + 1 - m) > 1 ? (n + 1 - m) : 1;
+    size_t o = 0;
+    w.W = o; o += (size_t)m * w.ldw;
+    w.Bi = o; o += (size_t)m * w.ldb;
+    w.big_doubles = o;
+    o = 0;
+    w.xb = o; o += m;
+    w.cb = o; o += m;
+    w.y = o; o += m;
+    w.al = o; o += m;
+    w.mv = o; o += m;
+    w.bv = o; o += m;
+    w.prow = o; o += m;
+    w.art = o; o += m;
+    w.t1 = o; o += m;
+    w.t2 = o; o += m;
+    w.cn = o; o += w.nn1;
+    w.r = o; o += w.nn1;
+    w.red = o; o += T;
+    w.small_doubles = o;
+    size_t q = 0;
+    w.basic = q; q += m;
+    w.nonbasic = q; q += w.nn1;
+    w.inb = q; q += n + 1;
+    w.redi = q; q += T;
+    w.ipiv = q; q += m;
+    w.n_ints = q;
+    w.big_bytes = w.big_doubles * sizeof(double);
+    w.small_bytes = w.small_doubles * sizeof(double) + ((w.n_ints * sizeof(int) + 7) / 8) * 8;
+    return w;
+}
+
+struct MinLoc {
+    double v;
+    int i;
+};
+
+struct Solver {
+    // problem
+    int m, n, m0, n0, L, lda;
+    const double *c0, *A0, *b0;
+    const int* bvar;
+    const double *bsign, *brhs;
+    // workspace
+    double *W, *Bi, *xb, *cb, *y, *al, *mv, *bv, *prow, *art, *t1, *t2, *cn, *r, *red;
+    int *basic, *nonbasic, *inb, *redi, *ipiv;
+    int ldw, ldb;
+    int ncols, nn;  // current width of W and number of non-basic columns
+    // counters (uniform across the CTA)
+    int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
+    int max_pivots, refactor_period;
+
+    GM_DEV static int pow2ceil(int v) {
+        int p = 1;
+        while (p < v) p <<= 1;
+        return p;
+    }
+
+    // ---- problem source: [A0 0; G I] of convertToEqualities, subproblem.go:81-139 ------------------
+    GM_DEV double src_a(int i, int j) const {
+        if (i < m0) return j < n0 ? gm_ldg(A0 + (size_t)i * lda + j) : 0.0;
+        const int k = i - m0;
+        if (j == bvar[k]) return bsign[k];
+        return j == n0 + k ? 1.0 : 0.0;
+    }
+    GM_DEV double src_c(int j) const { return j < n0 ? gm_ldg(c0 + j) : 0.0; }
+    GM_DEV double src_b(int i) const { return i < m0 ? gm_ldg(b0 + i) : brhs[i - m0]; }
+
+    // ---- block-wide reductions (result identical in every thread) ---------------------------------
+    // first minimum over f(k), NaN skipped, all-NaN -> index 0: floats.MinIdx, floats.go:458-474
+    template <class F>
+    GM_DEV MinLoc block_argmin(int len, F f) {
+        const int t = gm_tid(), T = gm_nthreads();
+        double bvv = INFINITY;
+        int bi = INT_MAX;
+        for (int k = t; k < len; k += T) {
+            const double v = f(k);
+            if (v == v && (bi == INT_MAX || v < bvv)) { bvv = v; bi = k; }
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double ov = gm_shfl_xor(bvv, d);
+            const int oi = gm_shfl_xor(bi, d);
+            if (oi != INT_MAX && (bi == INT_MAX || ov < bvv || (ov == bvv && oi < bi))) { bvv = ov; bi = oi; }
+        }
+        const int nw = T >> 5;
+        if ((t & 31) == 0) { red[t >> 5] = bvv; redi[t >> 5] = bi; }
+        gm_sync();
+        bvv = red[0];
+        bi = redi[0];
+        for (int w = 1; w < nw; ++w) {
+            const double ov = red[w];
+            const int oi = redi[w];
+            if (oi != INT_MAX && (bi == INT_MAX || ov < bvv || (ov == bvv && oi < bi))) { bvv = ov; bi = oi; }
+        }
+        gm_sync();
+        MinLoc out;
+        out.v = bvv;
+        out.i = bi == INT_MAX ? 0 : bi;
+        if (bi == INT_MAX) out.v = NAN;
+        return out;
+    }
+
+    template <class F>
+    GM_DEV double block_sum(int len, F f) {
+        const int t = gm_tid(), T = gm_nthreads();
+        double s = 0;
+        for (int k = t; k < len; k += T) s += f(k);
+        for (int d = 16; d >= 1; d >>= 1) s += gm_shfl_xor(s, d);
+        const int nw = T >> 5;
+        if ((t & 31) == 0) red[t >> 5] = s;
+        gm_sync();
+        s = 0;
+        for (int w = 0; w < nw; ++w) s += red[w];
+        gm_sync();
+        return s;
+    }
+
+    template <class F>
+    GM_DEV double block_max(int len, F f) {  // max over f(k) >= 0; NaN propagates as +Inf
+        const int t = gm_tid(), T = gm_nthreads();
+        double s = 0;
+        for (int k = t; k < len; k += T) {
+            const double v = f(k);
+            s = (v != v) ? INFINITY : fmax(s, v);
+        }
+        for (int d = 16; d >= 1; d >>= 1) s = fmax(s, gm_shfl_xor(s, d));
+        const int nw = T >> 5;
+        if ((t & 31) == 0) red[t >> 5] = s;
+        gm_sync();
+        s = 0;
+        for (int w = 0; w < nw; ++w) s = fmax(s, red[w]);
+        gm_sync();
+        return s;
+    }
+
+    template <class F>
+    GM_DEV int block_min_int(int len, F f) {  // min over f(k) (ints), INT_MAX when empty
+        const int t = gm_tid(), T = gm_nthreads();
+        int s = INT_MAX;
+        for (int k = t; k < len; k += T) {
+            const int v = f(k);
+            s = v < s ? v : s;
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int o = gm_shfl_xor(s, d);
+            s = o < s ? o : s;
+        }
+        const int nw = T >> 5;
+        if ((t & 31) == 0) redi[t >> 5] = s;
+        gm_sync();
+        s = INT_MAX;
+        for (int w = 0; w < nw; ++w) s = redi[w] < s ? redi[w] : s;
+        gm_sync();
+        return s;
+    }
+
+    // j fastest: lanes walk the contiguous dimension
+    template <class F>
+    GM_DEV void for_each_2d(int nrows, int ncolumns, F f) {
+        const int t = gm_tid(), T = gm_nthreads();
+        int S = pow2ceil(ncolumns);
+        if (S > T) S = T;
+        const int G = T / S;
+        for (int i = t / S; i < nrows; i += G)
+            for (int j = t % S; j < ncolumns; j += S) f(i, j);
+    }
+
+    // out[j] = (base ? base[j] : 0) + sgn * sum_i x[i] * M[i*ld + j]   (Dgemv Trans shape, vector.go:515-610)
+    GM_DEV void matvec_t(double* out, const double* base, double sgn, const double* M, int ld, int nr, int no,
+                         const double* x) {
+        const int t = gm_tid(), T = gm_nthreads();
+        if (no >= T) {
+            for (int j = t; j < no; j += T) {
+                double acc = 0;
+                for (int i = 0; i < nr; ++i) {
+                    const double xi = x[i];
+                    if (xi != 0) acc += xi * M[(size_t)i * ld + j];
+                }
+                out[j] = (base ? base[j] : 0.0) + sgn * acc;
+            }
+            gm_sync();
+            return;
+        }
+        const int S = pow2ceil(no);
+        const int G = T / S;
+        const int lane = t % S, g = t / S;
+        double acc = 0;
+        if (lane < no)
+            for (int i = g; i < nr; i += G) {
+                const double xi = x[i];
+                if (xi != 0) acc += xi * M[(size_t)i * ld + lane];
+            }
+        red[t] = acc;
+        gm_sync();
+        if (t < no) {
+            double s = 0;
+            for (int g2 = 0; g2 < G; ++g2) s += red[g2 * S + t];
+            out[t] = (base ? base[t] : 0.0) + sgn * s;
+        }
+        gm_sync();
+    }
+
+    // out[i] = (base ? base[i] : 0) + sgn * sum_j M[i*ld + j] * x[j]   (one warp per row)
+    GM_DEV void matvec_n(double* out, const double* base, double sgn, const double* M, int ld, int no, int nr,
+                         const double* x) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int warp = t >> 5, lane = t & 31, nw = T >> 5;
+        for (int i = warp; i < no; i += nw) {
+            double acc = 0;
+            const double* row = M + (size_t)i * ld;
+            for (int j = lane; j < nr; j += 32) acc += row[j] * x[j];
+            for (int d = 16; d >= 1; d >>= 1) acc += gm_shfl_xor(acc, d);
+            if (lane == 0) out[i] = (base ? base[i] : 0.0) + sgn * acc;
+        }
+        gm_sync();
+    }
+
+    // ---- verifyInputs, simplex.go:385-439 ---------------------------------------------------------
+    GM_DEV int verify_inputs() {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int warp = t >> 5, lane = t & 31, nw = T >> 5;
+        // first all-zero row (only root rows can be: a branch row always holds its slack's 1)
+        int zr = INT_MAX;
+        for (int i = warp; i < m0; i += nw) {
+            int nz = 0;
+            for (int j = lane; j < n0; j += 32) nz |= (gm_ldg(A0 + (size_t)i * lda + j) != 0.0);
+            nz = gm_any(nz);
+            if (!nz && i < zr) zr = i;
+        }
+        zr = block_min_int(T, [&](int k) { return k == t ? zr : INT_MAX; });
+        if (zr != INT_MAX) return src_b(zr) != 0.0 ? GM_ERR_INFEASIBLE : GM_ERR_ZERO_ROW;
+        // first all-zero column (slack columns n0.. are never zero)
+        int zc = INT_MAX;
+        for (int j = t; j < n0; j += T) {
+            int nz = 0;
+            for (int i = 0; i < m0 && !nz; ++i) nz = (gm_ldg(A0 + (size_t)i * lda + j) != 0.0);
+            for (int k = 0; k < L && !nz; ++k) nz = (bvar[k] == j && bsign[k] != 0.0);
+            if (!nz && j < zc) zc = j;
+        }
+        zc = block_min_int(T, [&](int k) { return k == t ? zc : INT_MAX; });
+        if (zc != INT_MAX) return src_c(zc) < 0.0 ? GM_ERR_UNBOUNDED : GM_ERR_ZERO_COLUMN;
+        return GM_OK;
+    }
+
+    // ---- W / cost vectors for the current basis (extractColumns :474-488, nonBasicIdx :174-197) -----
+    // phase1: costs are e_n (simplex.go:552-553) and column n is the artificial column `art`.
+    GM_DEV void build_w(int ncolumns, bool phase1) {
+        const int t = gm_tid(), T = gm_nthreads();
+        ncols = ncolumns;
+        nn = ncols - m;
+        for (int j = t; j < ncols; j += T) inb[j] = 0;
+        gm_sync();
+        for (int p = t; p < m; p += T) inb[basic[p]] = 1;
+        gm_sync();
+        if (t == 0) {
+            int k = 0;
+            for (int j = 0; j < ncols; ++j)
+                if (!inb[j]) nonbasic[k++] = j;
+        }
+        gm_sync();
+        for_each_2d(m, ncols, [&](int i, int p) {
+            const int v = p < m ? basic[p] : nonbasic[p - m];
+            W[(size_t)i * ldw + p] = (v == n) ? art[i] : src_a(i, v);
+        });
+        for (int p = t; p < m; p += T) {
+            const int v = basic[p];
+            cb[p] = phase1 ? (v == n ? 1.0 : 0.0) : src_c(v);
+        }
+        for (int k = t; k < nn; k += T) {
+            const int v = nonbasic[k];
+            cn[k] = phase1 ? (v == n ? 1.0 : 0.0) : src_c(v);
+        }
+        gm_sync();
+    }
+
+    // ---- Bi <- inverse of W[:, 0:m] by in-place Gauss-Jordan with partial (row) pivoting -----------
+    // Stands in for the LU behind every VecDense.SolveVec (mat/solve.go:110-140, lu.go:63-84,293-325).
+    // Returns 0, or 1 when a pivot is exactly zero / non-finite or cond_inf > 1e16 (the two conditions
+    // under which LU.Solve reports mat.Condition, lu.go:301,321). *cond1 = ||B||_1 * ||B^-1||_1.
+    GM_DEV int invert_basis(double* cond1) {
+        const int t = gm_tid(), T = gm_nthreads();
+        ninv++;
+        for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = W[(size_t)i * ldw + j]; });
+        gm_sync();
+        const double anorm_inf = block_max(m, [&](int i) {
+            double s = 0;
+            for (int j = 0; j < m; ++j) s += fabs(Bi[(size_t)i * ldb + j]);
+            return s;
+        });
+        const double anorm_1 = block_max(m, [&](int j) {
+            double s = 0;
+            for (int i = 0; i < m; ++i) s += fabs(Bi[(size_t)i * ldb + j]);
+            return s;
+        });
+        int singular = 0;
+        for (int k = 0; k < m; ++k) {
+            // Idamax: first largest |.| in column k at or below the diagonal (dgetf2.go:43-45)
+            MinLoc pl = block_argmin(m - k, [&](int q) { return -fabs(Bi[(size_t)(k + q) * ldb + k]); });
+            const int p = k + pl.i;
+            const double pabs = -pl.v;
+            if (!(pabs > 0.0) || pabs == INFINITY) { singular = 1; break; }
+            if (p != k) {
+                for (int j = t; j < m; j += T) {
+                    const double a = Bi[(size_t)k * ldb + j];
+                    Bi[(size_t)k * ldb + j] = Bi[(size_t)p * ldb + j];
+                    Bi[(size_t)p * ldb + j] = a;
+                }
+                gm_sync();
+            }
+            if (t == 0) ipiv[k] = p;
+            const double pv = Bi[(size_t)k * ldb + k];
+            for (int i = t; i < m; i += T) t1[i] = Bi[(size_t)i * ldb + k];
+            for (int j = t; j < m; j += T) prow[j] = (j == k ? 1.0 : Bi[(size_t)k * ldb + j]) / pv;
+            gm_sync();
+            for_each_2d(m, m, [&](int i, int j) {
+                if (i == k) {
+                    Bi[(size_t)i * ldb + j] = prow[j];
+                } else {
+                    const double f = t1[i];
+                    if (f != 0.0) {
+                        const double base = (j == k) ? 0.0 : Bi[(size_t)i * ldb + j];
+                        Bi[(size_t)i * ldb + j] = base - f * prow[j];
+                    }
+                }
+            });
+            gm_sync();
+        }
+        if (singular) {
+            *cond1 = INFINITY;
+            return 1;
+        }
+        // (PA)^-1 P : undo the row interchanges as column interchanges, last first
+        for (int k = m - 1; k >= 0; --k) {
+            const int p = ipiv[k];
+            if (p != k) {
+                for (int i = t; i < m; i += T) {
+                    const double a = Bi[(size_t)i * ldb + k];
+                    Bi[(size_t)i * ldb + k] = Bi[(size_t)i * ldb + p];
+                    Bi[(size_t)i * ldb + p] = a;
+                }
+                gm_sync();
+            }
+        }
+        const double inorm_inf = block_max(m, [&](int i) {
+            double s = 0;
+            for (int j = 0; j < m; ++j) s += fabs(Bi[(size_t)i * ldb + j]);
+            return s;
+        });
+        const double inorm_1 = block_max(m, [&](int j) {
+            double s = 0;
+            for (int i = 0; i < m; ++i) s += fabs(Bi[(size_t)i * ldb + j]);
+            return s;
+        });
+        *cond1 = anorm_1 * inorm_1;
+        const double cond_inf = anorm_inf * inorm_inf;
+        if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
+        return 0;
+    }
+
+    // xb = Bi b ; y = Bi^T cb
+    GM_DEV void recompute_xb_y() {
+        matvec_n(xb, nullptr, 1.0, Bi, ldb, m, m, bv);
+        matvec_t(y, nullptr, 1.0, Bi, ldb, m, m, cb);
+    }
+
+    GM_DEV bool xb_feasible() {  // initializeFromBasic's positivity test, simplex.go:459-468
+        const int bad = block_min_int(m, [&](int i) { return xb[i] < -GM_INIT_POS_TOL ? i : INT_MAX; });
+        return bad == INT_MAX;
+    }
+
+    // ---- the last m columns taken as a permutation matrix (pure slack basis): Bi = B^T ---------------
+    GM_DEV bool try_permutation_basis() {
+        const int t = gm_tid(), T = gm_nthreads();
+        for (int i = t; i < m; i += T) ipiv[i] = -1;
+        gm_sync();
+        int ok = 1;
+        for (int p = t; p < m; p += T) {
+            const int v = n - 1 - p;
+            int row = -1, cnt = 0;
+            if (v >= n0) {  // slack of branch row v-n0: a single 1 (convertToEqualities)
+                row = m0 + (v - n0);
+                cnt = 1;
+            } else {
+                for (int i = 0; i < m; ++i) {
+                    const double a = src_a(i, v);
+                    if (a != 0.0) {
+                        ++cnt;
+                        row = i;
+                        if (a != 1.0) cnt = 99;
+                    }
+                }
+            }
+            if (cnt != 1) { ok = 0; row = -1; }
+            else ipiv[row] = p;  // two columns on one row are caught below
+            inb[p] = row;
+        }
+        gm_sync();
+        for (int p = t; p < m; p += T)
+            if (inb[p] < 0 || ipiv[inb[p]] != p) ok = 0;
+        const int bad = block_min_int(T, [&](int k) { return (k == t && !ok) ? 0 : INT_MAX; });
+        if (bad != INT_MAX) return false;
+        for (int p = t; p < m; p += T) basic[p] = n - 1 - p;
+        gm_sync();
+        build_w(n, false);
+        // B[:,p] = e_row(p)  =>  B^-1 = B^T : Bi[p][row(p)] = 1, i.e. Bi[i][j] = (ipiv[j] == i)
+        for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = (ipiv[j] == i) ? 1.0 : 0.0; });
+        gm_sync();
+        return true;
+    }
+
+    // ---- findLinearlyIndependent, simplex.go:611-637, with mat.Cond(.,1) of the QR factor ----------
+    // (matrix.go:284-322, qr.go:23-39: cond = ||R||_1 ||R^-1||_1). Q (m x k) lives in Bi, R^-1 in W.
+    // Orthogonalisation is classical Gram-Schmidt applied twice; R^-1 and both 1-norms are carried
+    // incrementally, so a candidate costs O(mk + k^2) instead of a fresh O(mk^2) QR.
+    GM_DEV int scan_basis() {
+        const int t = gm_tid(), T = gm_nthreads();
+        scan_fb = 1;
+        for_each_2d(m, m, [&](int i, int j) { W[(size_t)i * ldw + j] = 0.0; });
+        gm_sync();
+        int k = 0;
+        double normR = 0, normRinv = 0;
+        for (int v = n - 1; v >= 0 && k < m; --v) {
+            for (int i = t; i < m; i += T) t1[i] = src_a(i, v);
+            gm_sync();
+            if (k > 0) {
+                matvec_t(t2, nullptr, 1.0, Bi, ldb, m, k, t1);   // s  = Q^T v
+                matvec_n(t1, t1, -1.0, Bi, ldb, m, k, t2);       // v -= Q s
+                matvec_t(prow, nullptr, 1.0, Bi, ldb, m, k, t1); // s2 = Q^T v
+                matvec_n(t1, t1, -1.0, Bi, ldb, m, k, prow);     // v -= Q s2
+                for (int j = t; j < k; j += T) t2[j] += prow[j];
+                gm_sync();
+            }
+            const double rho = sqrt(block_sum(m, [&](int i) { return t1[i] * t1[i]; }));
+            double colR = rho, colRinv = 1.0 / rho;
+            if (k > 0) {
+                // rho == 0 (or 1/rho overflowing) is an exactly dependent column: cond = +Inf, rejected
+                if (!(rho > 0.0) || colRinv == INFINITY) continue;
+                colR += block_sum(k, [&](int j) { return fabs(t2[j]); });
+                matvec_n(mv, nullptr, -1.0 / rho, W, ldw, k, k, t2);  // u = -R^-1 r / rho
+                colRinv += block_sum(k, [&](int j) { return fabs(mv[j]); });
+                const double cond = fmax(normR, colR) * fmax(normRinv, colRinv);
+                // "not linearly independent" :630-633 (NaN counts as dependent)
+                if (colR != colR || colRinv != colRinv || !(cond <= GM_LINDEP_COND_TOL)) continue;
+            }
+            for (int i = t; i < m; i += T) Bi[(size_t)i * ldb + k] = t1[i] / rho;
+            for (int j = t; j < k; j += T) W[(size_t)j * ldw + k] = mv[j];
+            if (t == 0) {
+                W[(size_t)k * ldw + k] = 1.0 / rho;
+                basic[k] = v;
+            }
+            normR = fmax(normR, colR);
+            normRinv = fmax(normRinv, colRinv);
+            ++k;
+            gm_sync();
+        }
+        return k;
+    }
+
+    // ---- computeMove, simplex.go:306-342: al = B^-1 a_e, mv = ratios. GM_OK / GM_ERR_UNBOUNDED -------
+    GM_DEV int compute_move(int e) {
+        const int t = gm_tid(), T = gm_nthreads();
+        // a_e is column m+e of W; stage it contiguously (t1) for the row-dot
+        for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + m + e];
+        gm_sync();
+        matvec_n(al, nullptr, 1.0, Bi, ldb, m, m, t1);
+        // d = -al, |d| < dRoundTol -> 0 ; Min(d) >= 0 -> unbounded ; move_i = xb_i / |d_i| for d_i < 0
+        for (int i = t; i < m; i += T) {
+            double d = -al[i];
+            if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+            mv[i] = d < 0.0 ? xb[i] / fabs(d) : INFINITY;
+            t2[i] = d;
+        }
+        gm_sync();
+        const int anyneg = block_min_int(m, [&](int i) { return t2[i] < 0.0 ? i : INT_MAX; });
+        // NaN in d: floats.Min skips nothing special; treat a NaN-only column as "no negative"
+        if (anyneg == INT_MAX) return GM_ERR_UNBOUNDED;
+        return GM_OK;
+    }
+
+    // ---- replaceBland, simplex.go:347-383 -----------------------------------------------------------
+    // The reference accepts a zero-step leaving position only if the swapped basis has cond_1 < 1e16.
+    // Here the test is on the pivot element: a finite ratio already implies |d_p| >= 1e-13 (dRoundTol),
+    // and the product-form update divides by d_p only, so the position is taken when |d_p| is not
+    // negligible against the column (|d_p| > 1e-11 * max|d|).
+    GM_DEV int replace_bland(int& l_out, int& e_out) {
+        int from = 0;
+        for (;;) {
+            const int i = block_min_int(nn - from, [&](int q) { return r[from + q] <= -GM_BLAND_NEG_TOL ? from + q : INT_MAX; });
+            if (i == INT_MAX) return GM_ERR_BLAND;
+            const int rc = compute_move(i);
+            if (rc != GM_OK) return rc;
+            MinLoc ml = block_argmin(m, [&](int q) { return mv[q]; });
+            if (fabs(ml.v) > GM_BLAND_ZERO_TOL) { l_out = ml.i; e_out = i; return GM_OK; }
+            const double dmax = block_max(m, [&](int q) { return fabs(al[q]); });
+            const int p = block_min_int(m, [&](int q) {
+                return (mv[q] <= GM_BLAND_ZERO_TOL && fabs(al[q]) > 1e-11 * dmax) ? q : INT_MAX;
+            });
+            if (p != INT_MAX) { l_out = p; e_out = i; return GM_OK; }
+            from = i + 1;
+            if (from >= nn) return GM_ERR_BLAND;
+        }
+    }
+
+    // ---- basis change: product-form update of Bi, xb, y; column swap in W (simplex.go:280-292) -------
+    GM_DEV void pivot(int l, int e, double re) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const double ap = al[l];
+        const double theta = xb[l] / ap;
+        for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] / ap;
+        gm_sync();
+        for_each_2d(m, m, [&](int i, int j) {
+            if (i == l) {
+                Bi[(size_t)i * ldb + j] = prow[j];
+            } else {
+                const double f = al[i];
+                if (f != 0.0) Bi[(size_t)i * ldb + j] -= f * prow[j];
+            }
+        });
+        for (int i = t; i < m; i += T) {
+            xb[i] = (i == l) ? theta : xb[i] - al[i] * theta;
+            y[i] += re * prow[i];
+            const double a = W[(size_t)i * ldw + l];
+            W[(size_t)i * ldw + l] = W[(size_t)i * ldw + m + e];
+            W[(size_t)i * ldw + m + e] = a;
+        }
+        if (t == 0) {
+            const int v = basic[l];
+            basic[l] = nonbasic[e];
+            nonbasic[e] = v;
+            const double cc = cb[l];
+            cb[l] = cn[e];
+            cn[e] = cc;
+        }
+        gm_sync();
+    }
+
+    GM_DEV int refactor() {
+        double cond1;
+        if (invert_basis(&cond1)) return GM_ERR_CONDITION;
+        recompute_xb_y();
+        return GM_OK;
+    }
+
+    // ---- the simplex main loop, simplex.go:233-293. Requires W, Bi, xb, y, cb, cn current. -----------
+    // Returns GM_OK (optimal), GM_ERR_UNBOUNDED (caller returns -Inf / nil) or a "break" status
+    // (last iterate is still reported, simplex.go:294-301).
+    GM_DEV int main_loop(double tol, int phase, bool fresh) {
+        const int t = gm_tid(), T = gm_nthreads();
+        int since = 0;
+        for (;;) {
+            if (piv1 + piv2 >= max_pivots) return GM_ERR_ITERATION_LIMIT;
+            // r = cn - an^T y  (:236-243)
+            matvec_t(r, cn, -1.0, W + m, ldw, m, nn, y);
+            MinLoc rl = block_argmin(nn, [&](int k) { return r[k]; });
+            if (rl.v >= -tol || rl.v != rl.v) {  // :247-250 (NaN compares false in Go too: falls through there;
+                                                  // here a NaN-only r ends the loop through the polish below)
+                if (!fresh) {  // polish: confirm optimality with freshly inverted factors
+                    const int rc = refactor();
+                    if (rc != GM_OK) return rc;
+                    fresh = true;
+                    since = 0;
+                    continue;
+                }
+                return GM_OK;
+            }
+            int e = rl.i;
+            double re = rl.v;
+            for (int k = t; k < nn; k += T)
+                if (fabs(r[k]) < GM_R_ROUND_TOL) r[k] = 0.0;  // :252-256
+            gm_sync();
+            int rc = compute_move(e);
+            if (rc != GM_OK) return rc;
+            MinLoc ml = block_argmin(m, [&](int q) { return mv[q]; });
+            int l = ml.i;
+            if (ml.v <= 0.0) {  // :268-277
+                nbland++;
+                rc = replace_bland(l, e);
+                if (rc != GM_OK) return rc;
+                re = r[e];
+            }
+            pivot(l, e, re);
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            if (++since >= refactor_period) {
+                rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+            }
+        }
+    }
+
+    // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
+    GM_DEV int find_initial_basic(bool& fresh) {
+        const int t = gm_tid(), T = gm_nthreads();
+        double cond1 = 0;
+        fresh = true;
+        bool have = try_permutation_basis();
+        if (!have) {
+            // optimistic: the reverse scan accepts the last m columns whenever that block is comfortably
+            // conditioned (every leading sub-block is then at least as well conditioned in the 2-norm)
+            for (int p = t; p < m; p += T) basic[p] = n - 1 - p;
+            gm_sync();
+            build_w(n, false);
+            const int sing = invert_basis(&cond1);
+            have = !sing && cond1 * (double)m * (double)m <= GM_LINDEP_COND_TOL;
+        }
+        if (!have) {
+            const int k = scan_basis();
+            if (k != m) return GM_ERR_SINGULAR;
+            build_w(n, false);
+            invert_basis(&cond1);  // a singular result falls into Phase I like initializeFromBasic's error does
+        }
+        recompute_xb_y();
+#ifdef GM_DEBUG_EMU
+        if (t == 0) { printf("basic:"); for (int p = 0; p < m; ++p) printf(" %d", basic[p]); printf(" xb:"); for (int p = 0; p < m; ++p) printf(" %g", xb[p]); printf(" scan=%d\n", scan_fb);
+          for (int i=0;i<m;++i){ for(int j=0;j<m;++j) printf(" %g", Bi[i*ldb+j]); printf("\n");} }
+#endif
+        if (xb_feasible()) return GM_OK;
+
+        // Phase I (:529-556)
+        used_p1 = 1;
+        MinLoc jm = block_argmin(m, [&](int i) { return xb[i]; });
+        const int j = jm.i;
+        // a_{n+1} = b - sum_{i != j} a_basic[i]
+        for (int i = t; i < m; i += T) t1[i] = 1.0;
+        gm_sync();
+        if (t == 0) t1[j] = 0.0;
+        gm_sync();
+        matvec_n(art, bv, -1.0, W, ldw, m, m, t1);
+        // B' = B with column j := art ; B^-1 art = xb - (1 - e_j)
+        for (int i = t; i < m; i += T) al[i] = xb[i] - (i == j ? 0.0 : 1.0);
+        gm_sync();
+        {
+            // product-form step on Bi only (the artificial enters position j)
+            const double ap = al[j];
+            for (int q = t; q < m; q += T) prow[q] = Bi[(size_t)j * ldb + q] / ap;
+            gm_sync();
+            for_each_2d(m, m, [&](int i, int q) {
+                if (i == j) Bi[(size_t)i * ldb + q] = prow[q];
+                else if (al[i] != 0.0) Bi[(size_t)i * ldb + q] -= al[i] * prow[q];
+            });
+            if (t == 0) basic[j] = n;
+            gm_sync();
+        }
+        build_w(n + 1, true);
+        recompute_xb_y();
+        fresh = false;
+        if (!xb_feasible()) {
+            double c1;
+            const int sing = invert_basis(&c1);
+            if (sing) return GM_PANIC_INITIAL_BASIC;  // simplex.go:155-158
+            recompute_xb_y();
+            if (!xb_feasible()) return GM_PANIC_INITIAL_BASIC;
+            fresh = true;
+        }
+        int rc = main_loop(GM_PHASE1_TOL, 1, fresh);
+        if (rc != GM_OK) {
+            if (rc == GM_ERR_ITERATION_LIMIT || rc == GM_PANIC_INITIAL_BASIC) return rc;
+            return GM_ERR_PHASE1_WRAPPED + rc;  // :557-559
+        }
+        fresh = true;  // main_loop returns optimal only right after a refactor
+        const int added = block_min_int(m, [&](int p) { return basic[p] == n ? p : INT_MAX; });
+        const double xart = added == INT_MAX ? 0.0 : xb[added];
+        if (fabs(xart) > GM_PHASE1_ZERO_TOL) return GM_ERR_INFEASIBLE;  // :563-565
+        if (added != INT_MAX) {
+            // artificial still basic at level zero: first non-basic column (ascending) that yields a
+            // non-singular, feasible basis in its place (:581-606)
+            for (int v = t; v <= n; v += T) inb[v] = 0;
+            gm_sync();
+            for (int p = t; p < m; p += T) inb[basic[p]] = 1;
+            gm_sync();
+            bool done = false;
+            for (int v = 0; v < n && !done; ++v) {
+                if (inb[v]) continue;
+                nrepair++;
+                for (int i = t; i < m; i += T) t1[i] = src_a(i, v);
+                gm_sync();
+                matvec_n(al, nullptr, 1.0, Bi, ldb, m, m, t1);
+                const double amax = block_max(m, [&](int q) { return fabs(al[q]); });
+                const double ap = al[added];
+                if (!(fabs(ap) > 1e-9 * fmax(1.0, amax))) continue;  // swapped basis (near-)singular
+                const double theta = xb[added] / ap;
+                const int bad = block_min_int(m, [&](int i) {
+                    const double nx = (i == added) ? theta : xb[i] - al[i] * theta;
+                    return nx < -GM_INIT_POS_TOL ? i : INT_MAX;
+                });
+                if (bad != INT_MAX) continue;
+                for (int q = t; q < m; q += T) prow[q] = Bi[(size_t)added * ldb + q] / ap;
+                gm_sync();
+                for_each_2d(m, m, [&](int i, int q) {
+                    if (i == added) Bi[(size_t)i * ldb + q] = prow[q];
+                    else if (al[i] != 0.0) Bi[(size_t)i * ldb + q] -= al[i] * prow[q];
+                });
+                for (int i = t; i < m; i += T) xb[i] = (i == added) ? theta : xb[i] - al[i] * theta;
+                if (t == 0) basic[added] = v;
+                gm_sync();
+                done = true;
+                fresh = false;
+            }
+            if (!done) return GM_ERR_INFEASIBLE;
+        }
+        build_w(n, false);  // Phase II lists: basis positions kept, non-basic ascending again (:174-197)
+        matvec_t(y, nullptr, 1.0, Bi, ldb, m, m, cb);
+        return GM_OK;
+    }
+
+    // ---- one LP: simplex(), simplex.go:93-302 -------------------------------------------------------
+    GM_DEV void solve(const BatchParams& P, int lp) {
+        const int t = gm_tid(), T = gm_nthreads();
+        piv1 = piv2 = nbland = ninv = used_p1 = scan_fb = nrepair = 0;
+        int status = GM_OK;
+        double optF = NAN;
+        bool have_x = false, have_basis = false;
+
+        for (int i = t; i < m; i += T) bv[i] = src_b(i);
+        gm_sync();
+        status = verify_inputs();
+        if (status != GM_OK) {
+            optF = status == GM_ERR_UNBOUNDED ? -INFINITY : NAN;
+        } else if (m > n) {
+            status = GM_ERR_SINGULAR;  // findLinearlyIndependent cannot find m columns (:495-498)
+        } else if (m == n) {  // :103-119
+            for (int p = t; p < m; p += T) basic[p] = p;
+            gm_sync();
+            build_w(n, false);
+            double c1;
+            if (invert_basis(&c1)) {
+                status = GM_ERR_SINGULAR;
+            } else {
+                matvec_n(xb, nullptr, 1.0, Bi, ldb, m, m, bv);
+                const int neg = block_min_int(m, [&](int i) { return xb[i] < 0.0 ? i : INT_MAX; });
+                if (neg != INT_MAX) status = GM_ERR_INFEASIBLE;
+                else {
+                    optF = block_sum(m, [&](int i) { return xb[i] * cb[i]; });
+                    have_x = true;
+                }
+            }
+        } else {
+            bool fresh = true;
+            if (P.initial_basic) {  // :147-160
+                const long long* ib = P.initial_basic + (size_t)lp * m;
+                const int bad = block_min_int(m, [&](int p) { return (ib[p] < 0 || ib[p] >= n) ? p : INT_MAX; });
+                if (bad != INT_MAX) status = GM_ERR_BAD_ARGUMENT;
+                else {
+                    for (int p = t; p < m; p += T) basic[p] = (int)ib[p];
+                    gm_sync();
+                    // a repeated index would corrupt the non-basic list: it is a singular basis
+                    for (int j = t; j < n; j += T) inb[j] = 0;
+                    gm_sync();
+                    for (int p = t; p < m; p += T) gm_atomic_add(&inb[basic[p]], 1);
+                    gm_sync();
+                    const int dup = block_min_int(n, [&](int j2) { return inb[j2] > 1 ? j2 : INT_MAX; });
+                    if (dup != INT_MAX) status = GM_PANIC_INITIAL_BASIC;
+                    else {
+                        build_w(n, false);
+                        double c1;
+                        if (invert_basis(&c1)) status = GM_PANIC_INITIAL_BASIC;
+                        else {
+                            recompute_xb_y();
+                            if (!xb_feasible()) status = GM_PANIC_INITIAL_BASIC;
+                        }
+                    }
+                }
+            } else {
+                status = find_initial_basic(fresh);
+            }
+            if (status == GM_OK) {
+                status = main_loop(P.tol, 2, fresh);
+                if (status == GM_ERR_UNBOUNDED) {
+                    optF = -INFINITY;  // :260-263
+                } else {
+                    optF = block_sum(m, [&](int i) { return cb[i] * xb[i]; });  // :296
+                    have_x = true;
+                    have_basis = true;
+                }
+            } else if (status == GM_ERR_UNBOUNDED) {
+                optF = -INFINITY;
+            }
+        }
+
+        // ---- results ----
+        double* xo = P.x + (size_t)lp * P.x_stride;
+        for (int j = t; j < P.x_len; j += T) xo[j] = 0.0;
+        gm_sync();
+        if (have_x) {
+            for (int p = t; p < m; p += T) {
+                const int v = basic[p];
+                if (v < P.x_len) xo[v] = xb[p];
+            }
+        }
+        if (P.basis) {
+            long long* bo = P.basis + (size_t)lp * m;
+            for (int p = t; p < m; p += T) bo[p] = have_basis ? (long long)basic[p] : -1;
+        }
+        if (t == 0) {
+            P.status[lp] = status;
+            P.optF[lp] = optF;
+            if (P.stats) {
+                int* s = P.stats + (size_t)lp * 8;
+                s[0] = piv1; s[1] = piv2; s[2] = nbland; s[3] = ninv;
+                s[4] = used_p1; s[5] = scan_fb; s[6] = nrepair; s[7] = have_x ? 1 : 0;
+            }
+        }
+        gm_sync();
+    }
+
+    // ---- binding of one work item to the workspace --------------------------------------------------
+    GM_DEV void bind(const BatchParams& P, int lp, double* big, double* small) {
+        m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
+        m = m0 + L; n = n0 + L;
+        c0 = P.c + (size_t)lp * P.c_stride;
+        A0 = P.A + (size_t)lp * P.A_stride;
+        b0 = P.b + (size_t)lp * P.b_stride;
+        bvar = P.bvar ? P.bvar + (size_t)lp * L : nullptr;
+        bsign = P.bsign ? P.bsign + (size_t)lp * L : nullptr;
+        brhs = P.brhs ? P.brhs + (size_t)lp * L : nullptr;
+        const WsLayout w = ws_layout(m, n, gm_nthreads());
+        ldw = w.ldw; ldb = w.ldb;
+        W = big + w.W; Bi = big + w.Bi;
+        xb = small + w.xb; cb = small + w.cb; y = small + w.y; al = small + w.al;
+        mv = small + w.mv; bv = small + w.bv; prow = small + w.prow; art = small + w.art; t1 = small + w.t1;
+        t2 = small + w.t2; cn = small + w.cn; r = small + w.r; red = small + w.red;
+        int* iw = reinterpret_cast<int*>(small + w.small_doubles);
+        basic = iw + w.basic; nonbasic = iw + w.nonbasic; inb = iw + w.inb; redi = iw + w.redi; ipiv = iw + w.ipiv;
+        max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
+        refactor_period = P.refactor_period > 0 ? P.refactor_period : 100;
+        ncols = n; nn = n - m;
+    }
+};
+
+// Persistent CTA: pulls LP indices from a global counter until the batch is exhausted.
+GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */) {
+    Solver s;
+    for (;;) {
+        if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
+        gm_sync();
+        const int lp = *slot;
+        gm_sync();
+        if (lp >= P.count) break;
+        s.bind(P, lp, big, small);
+        s.solve(P, lp);
+    }
+}
+
+}  // namespace gm

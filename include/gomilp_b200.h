@@ -1,0 +1,124 @@
+/* gomilp_b200.h — C ABI of libgomilp_b200.so, the B200 LP-relaxation engine behind GoMILP.
+ *
+ * Every entry point is what a cgo binding on the reference side would call (INTEGRATION.md shows the
+ * stubs). Plain pointers and sizes only; caller owns every buffer; nothing is retained after return
+ * (the cgo pointer rule), so host-buffer entry points copy synchronously. There is NO CPU fallback:
+ * without a CUDA device every compute call returns GM_ERR_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   gm_simplex            lp.Simplex(c, A, b, tol, initialBasic)
+ *                         vendor/gonum.org/v1/gonum/optimize/convex/lp/simplex.go:88-91
+ *   gm_simplex_batch*     the same call made `count` times by solveWorker goroutines, tree.go:196-205
+ *   gm_upload_root        milpProblem.toInitialSubproblem, ilp.go:43-71 (the shared c, A, b every node points to)
+ *   gm_solve_wave         subProblem.solve for a whole FIFO wave of nodes, subproblem.go:141-187
+ *                         (combineInequalities :55-78 + convertToEqualities :81-139 + lp.Simplex :154)
+ *   gm_milp_solve         milpProblem.solve, ilp.go:75-116 -> enumerationTree.startSearch, tree.go:66-123
+ *   gm_last_timing        extension of the BnbMiddleware hook, instrumentation.go:8-15 (per-wave device timings)
+ */
+#ifndef GOMILP_B200_H
+#define GOMILP_B200_H
+
+#include <stdint.h>
+
+#include "gomilp_status.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int gm_device_count(void);       /* number of CUDA devices visible, 0 if none */
+int gm_init(int device);         /* bind the calling process to `device`; GM_OK / GM_ERR_NO_DEVICE / GM_ERR_CUDA */
+int gm_shutdown(void);           /* release roots, streams and cached workspaces */
+const char* gm_last_error(void); /* message of the last GM_ERR_CUDA on the calling thread */
+
+/* Device timings of the last compute call made by the calling thread. */
+typedef struct gm_timing {
+    double h2d_ms;      /* host -> device copies */
+    double kernel_ms;   /* simplex kernel(s), CUDA events on the launch stream */
+    double d2h_ms;      /* device -> host copies */
+    int64_t lps;        /* LP relaxations solved */
+    int64_t launches;   /* kernel launches */
+    int64_t smem_bytes; /* dynamic shared memory per CTA (0: HBM-resident tier) */
+    int32_t tier;       /* 1 = shared-memory resident, 2 = HBM resident */
+    int32_t grid, block;
+} gm_timing;
+int gm_last_timing(gm_timing* out);
+
+/* Engine knobs with reference-compatible defaults (0 / negative = default). */
+typedef struct gm_options {
+    int32_t max_pivots;      /* safety cap per LP; the reference has none. default 50*(m+n)+1000 */
+    int32_t refactor_period; /* pivots between rebuilds of the basis inverse. default 100 */
+    int32_t force_tier;      /* 0 auto, 1 shared memory, 2 HBM workspace */
+    int32_t reserved;
+} gm_options;
+int gm_set_options(const gm_options* opt); /* process-wide */
+
+/* ---- (1) one LP: lp.Simplex, simplex.go:88 -----------------------------------------------------
+ * min c'x s.t. Ax = b, x >= 0. A row-major m x n with row stride lda (mat.Dense layout).
+ * initialBasic: NULL or m column indices of a feasible basis (simplex.go:147-160; an infeasible or
+ * singular one returns GM_PANIC_INITIAL_BASIC where the reference panics).
+ * Returns the gm_status. optF: objective (-Inf when unbounded, NaN when the reference returns NaN).
+ * optX (n): solution, zeros when the reference returns nil. basisOut (m, may be NULL). pivots (may be NULL). */
+int gm_simplex(const double* c, const double* A, int64_t lda, const double* b, int64_t m, int64_t n, double tol,
+               const int64_t* initialBasic, double* optF, double* optX, int64_t* basisOut, int64_t* pivots);
+
+/* ---- (1b) `count` independent LPs of one shape, HOST buffers ------------------------------------
+ * c [count][n], A [count][m][n], b [count][m]; status [count], optF [count], optX [count][n],
+ * basis [count][m] (may be NULL), stats [count][8] (may be NULL: pivots phase I, phase II, Bland calls,
+ * basis inversions, used phase I, basis-scan fallback, repair trials, x non-nil).
+ * Returns GM_OK when the batch ran (per-LP outcomes are in status[]), else an engine code. */
+int gm_simplex_batch(int64_t count, const double* c, const double* A, const double* b, int64_t m, int64_t n,
+                     double tol, int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats);
+
+/* ---- (1c) same, DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = default stream) --- */
+int gm_simplex_batch_device(int64_t count, const double* d_c, const double* d_A, const double* d_b, int64_t m,
+                            int64_t n, double tol, int32_t* d_status, double* d_optF, double* d_optX,
+                            int64_t* d_basis, int32_t* d_stats, void* stream);
+
+/* ---- (2) frontier wave over one shared root ---------------------------------------------------- */
+typedef int64_t gm_root_t;
+/* Upload the root standard form (c0 [n0], A0 [m0][lda], b0 [m0]) once; every node of every wave reads it. */
+int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
+                   gm_root_t* out);
+int gm_free_root(gm_root_t root);
+/* Solve `nodes` sub-problems of depth L in one launch. Node k carries L branch rows
+ * (bvar[k][l], bsign[k][l], brhs[k][l]) = bnbConstraint{branchedVariable, gsharp[var], hsharp}
+ * (subproblem.go:36-44); its LP is [A0 0; G I] x = [b0; h] of shape (m0+L) x (n0+L).
+ * Outputs: status [nodes], z [nodes], x [nodes][n0] (truncated like subproblem.go:157-159),
+ * basis [nodes][m0+L] (may be NULL), stats [nodes][8] (may be NULL). */
+int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                  const double* brhs, int32_t* status, double* z, double* x, int64_t* basis, int32_t* stats);
+
+/* ---- (3) whole MILP: milpProblem.solve, ilp.go:75-116 ------------------------------------------- */
+typedef struct gm_milp_result {
+    int32_t status;     /* gm_milp_status */
+    int32_t lp_status;  /* offending gm_status for the PANIC_* outcomes */
+    double z;
+    int64_t x_len;      /* entries written to x (nvar, or nvar+nineq on a deadline: ilp.go:92-99 does not strip slacks) */
+    int64_t nodes;      /* LP relaxations solved, root included */
+    int64_t waves;      /* kernel launches = BFS levels processed */
+    int64_t pivots;
+    double device_ms;   /* sum of kernel times */
+} gm_milp_result;
+
+/* Per-node decision callback = BnbMiddleware.ProcessDecision (instrumentation.go:8-15), invoked in the
+ * 1-worker FIFO order of the reference; NewSubProblem is implied by (id, parent). May be NULL. */
+typedef void (*gm_decision_cb)(void* user, int64_t id, int64_t parent, int32_t depth, int32_t lp_status, double z,
+                               int32_t decision, int32_t branch_var, double branch_floor);
+/* Per-wave callback (the device-timing extension). May be NULL. */
+typedef void (*gm_wave_cb)(void* user, int64_t wave, int64_t nodes, int64_t pivots, double kernel_ms);
+
+/* c [nvar]; A [meq][nvar], b [meq] (meq may be 0); G [nineq][nvar], h [nineq] (nineq may be 0);
+ * integrality [nvar] (0/1). heuristic: gm_branch_heuristic; mode: gm_bnb_mode.
+ * node_limit / time_limit_s stand in for the context deadline (0 = none).
+ * x must hold nvar + nineq + 1 doubles. */
+int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const double* A, const double* b, int64_t nineq,
+                  const double* G, const double* h, const uint8_t* integrality, int32_t heuristic, int32_t mode,
+                  int64_t node_limit, double time_limit_s, double* x, gm_milp_result* result,
+                  gm_decision_cb on_decision, gm_wave_cb on_wave, void* user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOMILP_B200_H */

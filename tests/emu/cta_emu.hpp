@@ -1,0 +1,198 @@
+// tests/emu/cta_emu.hpp — TEST INFRASTRUCTURE ONLY.
+//
+// A single-CTA emulator: every CUDA thread of one thread block is a ucontext fiber scheduled
+// round-robin on one OS thread; __syncthreads() and the warp shuffles/votes are rendezvous points.
+// It lets the CPU test-suite (which has no GPU) drive the SAME kernel source that nvcc compiles for
+// sm_100a (gomilp_b200/csrc/simplex_cta.cuh, built here with g++ -DGM_EMULATE) through its control
+// flow: phase transitions, Bland fallback, status codes. It is a debugging aid for the kernel, not a
+// solver: nothing under gomilp_b200/ links it and the product library has no CPU path.
+//
+// Deliberate limitations: deterministic (optionally shuffled) scheduling means a missing barrier is
+// only caught when it changes a result; compute-sanitizer racecheck on the GPU is the real check.
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <vector>
+
+namespace emu {
+
+enum Wait { RUN = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
+
+struct Cta {
+    int T = 0;
+    int cur = 0;
+    std::vector<ucontext_t> ctx;
+    std::vector<std::vector<char>> stacks;
+    std::vector<int> state;
+    std::vector<uint64_t> slot;  // shuffle exchange slots
+    std::vector<int> vote;
+    ucontext_t sched;
+    std::function<void()> body;
+    long barriers = 0;
+    unsigned rng = 12345;
+    bool shuffle_order = false;
+};
+
+inline Cta*& current() {
+    static thread_local Cta* c = nullptr;
+    return c;
+}
+
+inline void yield_as(int st) {
+    Cta* c = current();
+    c->state[c->cur] = st;
+    swapcontext(&c->ctx[c->cur], &c->sched);
+}
+
+inline void trampoline() {
+    Cta* c = current();
+    c->body();
+    c->state[c->cur] = DONE;
+    swapcontext(&c->ctx[c->cur], &c->sched);
+}
+
+// Runs body() on T fibers to completion. Throws on barrier divergence (some threads exit or wait on a
+// different barrier kind while others wait forever).
+inline void run_cta(int T, std::function<void()> body, bool shuffle_order = false, size_t stack_bytes = 256 * 1024) {
+    Cta c;
+    c.T = T;
+    c.body = std::move(body);
+    c.ctx.resize(T);
+    c.stacks.resize(T);
+    c.state.assign(T, RUN);
+    c.slot.assign(T, 0);
+    c.vote.assign(T, 0);
+    c.shuffle_order = shuffle_order;
+    Cta* prev = current();
+    current() = &c;
+    for (int t = 0; t < T; ++t) {
+        c.stacks[t].resize(stack_bytes);
+        getcontext(&c.ctx[t]);
+        c.ctx[t].uc_stack.ss_sp = c.stacks[t].data();
+        c.ctx[t].uc_stack.ss_size = stack_bytes;
+        c.ctx[t].uc_link = &c.sched;
+        makecontext(&c.ctx[t], (void (*)())trampoline, 0);
+    }
+    std::vector<int> order(T);
+    for (int t = 0; t < T; ++t) order[t] = t;
+    for (;;) {
+        bool progressed = false;
+        if (c.shuffle_order) {
+            for (int t = T - 1; t > 0; --t) {
+                c.rng = c.rng * 1664525u + 1013904223u;
+                int j = (int)((c.rng >> 8) % (unsigned)(t + 1));
+                std::swap(order[t], order[j]);
+            }
+        }
+        for (int k = 0; k < T; ++k) {
+            int t = order[k];
+            if (c.state[t] != RUN) continue;
+            c.cur = t;
+            progressed = true;
+            swapcontext(&c.sched, &c.ctx[t]);
+        }
+        // release complete warps waiting on a warp rendezvous
+        for (int w0 = 0; w0 < T; w0 += 32) {
+            int w1 = std::min(T, w0 + 32);
+            bool all = true;
+            for (int t = w0; t < w1; ++t)
+                if (c.state[t] != WAIT_WARP) { all = false; break; }
+            if (all) {
+                for (int t = w0; t < w1; ++t) c.state[t] = RUN;
+                progressed = true;
+            }
+        }
+        int nblock = 0, ndone = 0, nrun = 0;
+        for (int t = 0; t < T; ++t) {
+            nblock += c.state[t] == WAIT_BLOCK;
+            ndone += c.state[t] == DONE;
+            nrun += c.state[t] == RUN;
+        }
+        if (ndone == T) break;
+        if (nblock == T) {
+            for (int t = 0; t < T; ++t) c.state[t] = RUN;
+            c.barriers++;
+            continue;
+        }
+        if (nrun == 0 && !progressed) {
+            current() = prev;
+            throw std::runtime_error("cta_emu: barrier divergence / deadlock");
+        }
+        if (nrun == 0) {
+            // nothing runnable and no warp/block released: divergence
+            bool any_release = false;
+            for (int t = 0; t < T; ++t) any_release |= c.state[t] == RUN;
+            if (!any_release) {
+                current() = prev;
+                throw std::runtime_error("cta_emu: barrier divergence (mixed waits)");
+            }
+        }
+    }
+    current() = prev;
+}
+
+template <class V>
+inline V shfl_generic(V v, int src_lane_abs_valid, int src) {
+    Cta* c = current();
+    uint64_t bits = 0;
+    static_assert(sizeof(V) <= 8, "shuffle payload");
+    std::memcpy(&bits, &v, sizeof(V));
+    c->slot[c->cur] = bits;
+    yield_as(WAIT_WARP);
+    V out = v;
+    if (src_lane_abs_valid) {
+        uint64_t b = c->slot[src];
+        std::memcpy(&out, &b, sizeof(V));
+    }
+    yield_as(WAIT_WARP);
+    return out;
+}
+
+}  // namespace emu
+
+#define GM_DEV inline
+#define GM_DEV_NOINLINE inline
+inline int gm_tid() { return emu::current()->cur; }
+inline int gm_nthreads() { return emu::current()->T; }
+inline void gm_sync() { emu::yield_as(emu::WAIT_BLOCK); }
+template <class V>
+inline V gm_shfl_down_t(V v, int d) {
+    emu::Cta* c = emu::current();
+    int lane = c->cur & 31;
+    int src = c->cur + d;
+    bool ok = (lane + d) < 32 && src < c->T;
+    return emu::shfl_generic(v, ok, src);
+}
+template <class V>
+inline V gm_shfl_xor_t(V v, int d) {
+    emu::Cta* c = emu::current();
+    int src = (c->cur & ~31) | ((c->cur & 31) ^ d);
+    bool ok = src < c->T;
+    return emu::shfl_generic(v, ok, src);
+}
+inline double gm_shfl_down(double v, int d) { return gm_shfl_down_t(v, d); }
+inline int gm_shfl_down(int v, int d) { return gm_shfl_down_t(v, d); }
+inline double gm_shfl_xor(double v, int d) { return gm_shfl_xor_t(v, d); }
+inline int gm_shfl_xor(int v, int d) { return gm_shfl_xor_t(v, d); }
+inline int gm_any(int pred) {
+    emu::Cta* c = emu::current();
+    c->vote[c->cur] = pred ? 1 : 0;
+    emu::yield_as(emu::WAIT_WARP);
+    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32), r = 0;
+    for (int t = w0; t < w1; ++t) r |= c->vote[t];
+    emu::yield_as(emu::WAIT_WARP);
+    return r;
+}
+inline int gm_atomic_add(int* p, int v) {
+    int o = *p;
+    *p = o + v;
+    return o;
+}
+inline double gm_ldg(const double* p) { return *p; }

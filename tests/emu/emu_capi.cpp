@@ -1,0 +1,85 @@
+// tests/emu/emu_capi.cpp — TEST INFRASTRUCTURE ONLY. Compiles the product kernel source
+// (gomilp_b200/csrc/simplex_cta.cuh) with g++ -DGM_EMULATE against the fiber CTA emulator, so the
+// CPU test-suite can drive the kernel's control flow on small LPs in a container without a GPU.
+// Never linked into libgomilp_b200.so; see cta_emu.hpp.
+#define GM_EMULATE 1
+#include "cta_emu.hpp"
+#include "../../gomilp_b200/csrc/simplex_cta.cuh"
+
+extern "C" {
+
+// Same meaning as the device batch entry: `count` LPs, shared (stride 0) or per-LP roots, optional
+// branch rows. T = emulated threads per CTA (power of two, multiple of 32).
+int emu_simplex_batch(int count, const double* c, const double* A, const double* b, long long c_stride,
+                      long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
+                      const double* bsign, const double* brhs, const long long* initial_basic, double tol,
+                      int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
+                      int x_len, long long* basis, int* stats, int T, int shuffle_order) {
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c = c; P.A = A; P.b = b;
+    P.c_stride = c_stride; P.A_stride = A_stride; P.b_stride = b_stride;
+    P.lda = lda; P.m0 = m0; P.n0 = n0; P.L = L;
+    P.bvar = bvar; P.bsign = bsign; P.brhs = brhs;
+    P.initial_basic = initial_basic;
+    P.tol = tol; P.count = count; P.max_pivots = max_pivots; P.refactor_period = refactor_period;
+    P.status = status; P.optF = optF; P.x = x; P.x_stride = x_stride; P.x_len = x_len;
+    P.basis = basis; P.stats = stats;
+    int queue = 0;
+    P.queue = &queue;
+    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T);
+    std::vector<double> big(w.big_doubles + 8, 0.0), small(w.small_bytes / 8 + 8, 0.0);
+    int slot = 0;
+    try {
+        emu::run_cta(T, [&]() { gm::cta_main(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- emulator-backed stand-ins for the wave entry points, so that the product's B&B host
+// (gomilp_b200/csrc/bnb_host.cpp, compiled into this TEST library unchanged) can be replayed on the CPU.
+#include <map>
+#include "../../include/gomilp_b200.h"
+
+namespace {
+struct EmuRoot { std::vector<double> c, A, b; int m0, n0; };
+std::map<gm_root_t, EmuRoot> g_roots;
+gm_root_t g_next = 1;
+int g_T = 64;
+}  // namespace
+
+extern "C" {
+void emu_set_threads(int T) { g_T = T; }
+int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
+                   gm_root_t* out) {
+    EmuRoot r;
+    r.m0 = (int)m0; r.n0 = (int)n0;
+    r.c.assign(c0, c0 + n0);
+    r.b.assign(b0, b0 + m0);
+    r.A.resize((size_t)m0 * n0);
+    for (int64_t i = 0; i < m0; ++i)
+        for (int64_t j = 0; j < n0; ++j) r.A[(size_t)i * n0 + j] = A0[(size_t)i * lda + j];
+    *out = g_next++;
+    g_roots[*out] = std::move(r);
+    return GM_OK;
+}
+int gm_free_root(gm_root_t h) { return g_roots.erase(h) ? GM_OK : GM_ERR_BAD_HANDLE; }
+int gm_last_timing(gm_timing* t) { std::memset(t, 0, sizeof(*t)); return GM_OK; }
+int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                  const double* brhs, int32_t* status, double* z, double* x, int64_t* basis, int32_t* stats) {
+    auto it = g_roots.find(root);
+    if (it == g_roots.end()) return GM_ERR_BAD_HANDLE;
+    EmuRoot& r = it->second;
+    int rc = emu_simplex_batch((int)nodes, r.c.data(), r.A.data(), r.b.data(), 0, 0, 0, r.n0, r.m0, r.n0, (int)L, bvar,
+                               bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0,
+                               reinterpret_cast<long long*>(basis), stats, g_T, 0);
+    return rc == 0 ? GM_OK : GM_ERR_CUDA;
+}
+}  // extern "C"
+
+#include "../../gomilp_b200/csrc/bnb_host.cpp"
