@@ -1,0 +1,200 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI of libgomilp_b200.so, against the CPU oracle on the
+same seeded inputs and against the reference's golden vectors; at BASELINE.json's full C2 size through
+size-independent properties (primal feasibility, x >= 0, dual feasibility / optimality certificate).
+Tolerance: 1e-9 relative on objectives and primal values (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import gomilp_b200 as gm
+import oracle
+from gomilp_b200 import status as S
+from problems import (feasible_bounded_lp, knapsack, random_milp, raw_lp, reference_pins, standard_form)
+
+pytestmark = pytest.mark.gpu
+PINS = reference_pins()
+RTOL = 1e-9
+MILP_STATUS = {"OK": S.GM_MILP_OK, "DEADLINE": S.GM_MILP_DEADLINE_EXCEEDED,
+               "NO_INTEGER_FEASIBLE_SOLUTION": S.GM_MILP_NO_INTEGER_FEASIBLE_SOLUTION}
+
+
+def _close(a, b, tol=RTOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) <= tol
+
+
+def test_native_library_is_the_one_loaded():
+    assert gm.device_count() >= 1
+    gm.init(0)
+    with open("/proc/self/maps") as f:
+        assert "libgomilp_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("case", PINS["milp"], ids=[c["src"].split(" ")[0] for c in PINS["milp"]])
+def test_reference_milp_pins(case):
+    r = gm.milp_solve(case["c"], case["A"], case["b"], case["G"], case["h"], case["integrality"], node_limit=400)
+    assert r.status == MILP_STATUS[case["want_status"]]
+    if case["want_status"] == "OK":
+        assert _close(r.x, case["want_x"], 1e-12) and abs(r.z - case["want_z"]) <= 1e-12
+
+
+def test_reference_status_pins():
+    p = PINS["singular_16x14"]
+    assert gm.simplex(p["c"], p["A"], p["b"]).status == S.GM_ERR_SINGULAR
+    p = PINS["api_end_to_end"]
+    r = gm.milp_solve(p["c"], p["A"], p["b"], p["G"], p["h"], p["integrality"])
+    assert r.status == S.GM_MILP_OK and _close(r.x, p["want_x"], 1e-12)
+
+
+def test_single_lp_entry_point_and_status_taxonomy():
+    r = gm.simplex([-1, -2, 0, 0], [[-1, 2, 1, 0], [3, 1, 0, 1]], [4, 9])
+    assert r.status == S.GM_OK and r.optF == -8.0 and r.x.tolist() == [2, 3, 0, 0] and r.pivots == 2
+    A = np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0]])
+    assert gm.simplex([1, 1, 1], A, [1, 1]).status == S.GM_ERR_INFEASIBLE
+    assert gm.simplex([1, 1, 1], A, [1, 0]).status == S.GM_ERR_ZERO_ROW
+    A = np.array([[1.0, 0.0, 3.0], [2.0, 0.0, 1.0]])
+    assert gm.simplex([1, -1, 1], A, [1, 1]).status == S.GM_ERR_UNBOUNDED
+    assert gm.simplex([1, 1, 1], A, [1, 1]).status == S.GM_ERR_ZERO_COLUMN
+    r = gm.simplex([-1.0, 0.0], [[1.0, -1.0]], [1.0])
+    assert r.status == S.GM_ERR_UNBOUNDED and r.optF == -np.inf and r.x is None
+    r = gm.simplex([1.0, 1.0], [[2.0, 1.0], [1.0, 3.0]], [3.0, 4.0])  # m == n
+    assert r.status == S.GM_OK and _close(r.x, [1, 1]) and _close(r.optF, 2.0)
+    rng = np.random.default_rng(3)
+    c, A, b = feasible_bounded_lp(rng, 9, 20)
+    o = oracle.simplex(c, A, b)
+    w = gm.simplex(c, A, b, initial_basic=o.basis)  # warm start from the optimal basis: no pivots
+    assert w.status == S.GM_OK and w.pivots == 0 and _close(w.x, o.x) and _close(w.optF, o.optF)
+    assert gm.simplex(c, A, b, initial_basic=[0] * 9).status == S.GM_PANIC_INITIAL_BASIC
+
+
+@pytest.mark.parametrize("m,n,count", [(1, 2, 8), (2, 5, 64), (7, 19, 128), (16, 32, 256), (33, 70, 64),
+                                        (64, 128, 192), (64, 65, 16), (100, 180, 24)])
+def test_batch_matches_oracle(m, n, count):
+    rng = np.random.default_rng(1000 * m + n)
+    c, A, b = feasible_bounded_lp(rng, m, n, count)
+    g = gm.simplex_batch(c, A, b)
+    o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads())
+    assert (g["status"] == o["status"]).all() and (o["status"] == S.GM_OK).all()
+    assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
+    same_basis = np.mean([set(g["basis"][i]) == set(o["basis"][i]) for i in range(count)])
+    same_pivots = np.mean(g["pivots"] == o["pivots"])
+    print(f"m={m} n={n}: identical final basis {same_basis:.3f}, identical pivot count {same_pivots:.3f}")
+    assert same_basis >= 0.9
+
+
+def test_status_parity_on_raw_gaussian_lps():
+    rng = np.random.default_rng(77)
+    agree = total = 0
+    for (m, n, count, pz) in [(3, 7, 256, 0.0), (6, 10, 256, 0.3), (10, 24, 128, 0.0), (5, 5, 64, 0.0), (6, 4, 16, 0.0)]:
+        c, A, b = raw_lp(rng, m, n, count, pz)
+        g = gm.simplex_batch(c, A, b)
+        o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads(), max_pivots=20000)
+        total += count
+        agree += int((g["status"] == o["status"]).sum())
+        ok = (g["status"] == S.GM_OK) & (o["status"] == S.GM_OK)
+        if ok.any():
+            assert _close(g["optF"][ok], o["optF"][ok]) and _close(g["x"][ok], o["x"][ok])
+    print(f"status agreement {agree}/{total}")
+    assert agree >= total - 3  # continuous data: only noise-level ties (r_e = -1e-17 at tol 0) can differ
+
+
+def test_hbm_tier_matches_oracle():
+    """LPs too large for shared memory run the same kernel with W / Bi in an HBM workspace."""
+    rng = np.random.default_rng(5)
+    c, A, b = feasible_bounded_lp(rng, 150, 260, 6)
+    g = gm.simplex_batch(c, A, b)
+    assert gm.last_timing()["tier"] == 2
+    o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads())
+    assert (g["status"] == o["status"]).all()
+    assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
+    gm.set_options(force_tier=2)
+    try:
+        c, A, b = feasible_bounded_lp(rng, 16, 40, 32)
+        g = gm.simplex_batch(c, A, b)
+        o = oracle.simplex_batch(c, A, b)
+        assert (g["status"] == o["status"]).all() and _close(g["x"], o["x"])
+        gm.set_options(force_tier=3)
+        g = gm.simplex_batch(c, A, b)
+        assert (g["status"] == o["status"]).all() and _close(g["x"], o["x"])
+    finally:
+        gm.set_options()
+
+
+def test_wave_matches_oracle_children():
+    rng = np.random.default_rng(9)
+    p = random_milp(rng, 12, 6)
+    c0, A0, b0 = standard_form(p)
+    m0, n0 = A0.shape
+    L, nodes = 3, 64
+    bvar = rng.integers(0, 12, size=(nodes, L)).astype(np.int32)
+    bsign = rng.choice([-1.0, 1.0], size=(nodes, L))
+    brhs = np.where(bsign > 0, rng.integers(0, 4, size=(nodes, L)), -rng.integers(1, 3, size=(nodes, L))).astype(float)
+    root = gm.upload_root(c0, A0, b0)
+    try:
+        w = gm.solve_wave(root, n0, m0, bvar, bsign, brhs)
+    finally:
+        gm.free_root(root)
+    agree = 0
+    for k in range(nodes):
+        A = np.zeros((m0 + L, n0 + L))
+        A[:m0, :n0] = A0
+        for l in range(L):
+            A[m0 + l, bvar[k, l]] = bsign[k, l]
+            A[m0 + l, n0 + l] = 1.0
+        o = oracle.simplex(np.concatenate([c0, np.zeros(L)]), A, np.concatenate([b0, brhs[k]]))
+        agree += int(w.status[k] == o.status)
+        if o.status == S.GM_OK and w.status[k] == S.GM_OK:
+            assert _close(w.z[k], o.optF) and _close(w.x[k], o.x[:n0])
+    assert agree >= nodes - 1
+
+
+def test_milp_objective_matches_oracle_and_highs():
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    rng = np.random.default_rng(155)
+    same_tree = 0
+    cases = 12
+    for _ in range(cases):
+        p = random_milp(rng, int(rng.integers(3, 9)), int(rng.integers(1, 4)))
+        g = gm.milp_solve(p["c"], p["A"], p["b"], p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED,
+                          node_limit=4000)
+        o = oracle.bnb_solve(p["c"], p["A"], p["b"], p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED,
+                             node_limit=4000)
+        hs = milp(p["c"], constraints=LinearConstraint(p["G"], -np.inf, p["h"]), integrality=p["integrality"],
+                  bounds=Bounds(0, np.inf), options={"time_limit": 10})
+        assert g.status == S.GM_MILP_OK and hs.status == 0
+        assert abs(g.z - hs.fun) <= 0.005           # the reference's GLPK tolerance
+        if o.status == S.GM_MILP_OK:
+            assert abs(g.z - o.z) <= RTOL * max(1.0, abs(o.z))
+        same_tree += int(o.nodes == g.nodes)
+    print(f"identical node count as the oracle replay: {same_tree}/{cases}")
+
+
+def test_full_size_c2_batch_properties():
+    """BASELINE.json configs[1]: 4096 LPs, m=64, n=128. Oracle parity on a slice, optimality certificate on all."""
+    rng = np.random.default_rng(1234)
+    m, n, count = 64, 128, 4096
+    c, A, b = feasible_bounded_lp(rng, m, n, count)
+    g = gm.simplex_batch(c, A, b)
+    assert (g["status"] == S.GM_OK).all()
+    x = g["x"]
+    assert x.min() >= -1e-9
+    res = np.abs(np.einsum("kij,kj->ki", A, x) - b).max(axis=1)
+    assert res.max() <= 1e-8 * max(1.0, np.abs(b).max())
+    assert _close(g["optF"], np.einsum("kj,kj->k", c, x))
+    assert ((x != 0).sum(axis=1) <= m).all()  # basic solutions
+    # dual certificate: y = B^-T c_B gives reduced costs >= -1e-7 on every column
+    for k in range(0, count, 97):
+        B = A[k][:, g["basis"][k]]
+        y = np.linalg.solve(B.T, c[k][g["basis"][k]])
+        assert (c[k] - A[k].T @ y).min() >= -1e-7
+    sl = slice(0, 128)
+    o = oracle.simplex_batch(c[sl], A[sl], b[sl], threads=oracle.num_hw_threads())
+    assert _close(g["optF"][sl], o["optF"]) and _close(g["x"][sl], o["x"])
+
+
+def test_knapsack_wave_root_and_first_levels():
+    rng = np.random.default_rng(7)
+    p = knapsack(rng, 60, 8)
+    g = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, node_limit=64)
+    o = oracle.bnb_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, node_limit=64)
+    assert g.log[0][3] == S.GM_OK and abs(g.log[0][4] - o.log["z"][0]) <= RTOL * abs(o.log["z"][0])
+    assert g.status in (S.GM_MILP_OK, S.GM_MILP_DEADLINE_EXCEEDED)
