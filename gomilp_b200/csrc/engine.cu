@@ -193,6 +193,12 @@ int gm_init(int device) {
     g.device = device;
     g.sms = prop.multiProcessorCount;
     g.smem_optin = prop.sharedMemPerBlockOptin;
+    // keep stream-ordered allocations cached across calls (the default pool trims at every synchronize)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g.ready = true;
     return GM_OK;
 }
