@@ -272,11 +272,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "api": "gm_simplex_batch (C ABI, pinned host buffers)"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "simplex_wave_smem<256,2>", "launch_ms": launch_ms,
+                     "traffic": None, "kernel": "simplex_wave_reg<256,2>" if tm["tier"] == 1 else "simplex_wave_smem<256,2>", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_pivot": bytes_per_pivot(M, N),
                      "pivots_per_launch": pivots, "peak_source": peak_src,
-                     "note": "tier 1 keeps W and B^-1 in shared memory, so the algorithmic bytes never touch HBM; "
-                             "the binding resource is shared-memory bandwidth / barrier latency (see smem)",
+                     "note": "tier 1 keeps B^-1 in registers and W in shared memory, so the algorithmic bytes never "
+                             "touch HBM; the binding resources are issue slots / barrier latency (see smem)",
                      "smem": {"peak_gbs": smem_peak, "frac": achieved / smem_peak,
                               "peak_source": "148 SMs x 128 B/clk x median SM clock under load"}},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -16,15 +16,25 @@
 
 namespace {
 
-constexpr int kSmemThreads = 256;  // tier 1: one LP per CTA, everything in shared memory
-constexpr int kHbmThreads = 512;   // tier 2/3: W and Bi in HBM
+constexpr int kSmemThreads = 256;  // tiers 1, 2: one LP per CTA, W in shared memory
+constexpr int kHbmThreads = 512;   // tiers 3, 4: W and Bi in HBM
 
+// tier 1 (m <= 64): basis inverse in registers, W + staging tile + vectors in shared memory
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) simplex_wave_reg(gm::BatchParams P) {
+    extern __shared__ double smem[];
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, true);
+    gm::cta_main<true>(P, smem, smem + w.big_doubles, &slot);
+}
+
+// tier 2: W, Bi and vectors in shared memory
 template <int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) simplex_wave_smem(gm::BatchParams P) {
     extern __shared__ double smem[];
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
-    gm::cta_main(P, smem, smem + w.big_doubles, &slot);
+    gm::cta_main<false>(P, smem, smem + w.big_doubles, &slot);
 }
 
 // big part (W, Bi) in HBM, small part in shared memory
@@ -32,7 +42,7 @@ template <int T>
 __global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
     extern __shared__ double smem[];
     __shared__ int slot;
-    gm::cta_main(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, &slot);
+    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, &slot);
 }
 
 // everything in HBM (very large m + n)
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(T, 1) simplex_wave_hbm_all(gm::BatchParams P) 
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
     double* base = P.work + (size_t)blockIdx.x * P.work_stride;
-    gm::cta_main(P, base, base + w.big_doubles, &slot);
+    gm::cta_main<false>(P, base, base + w.big_doubles, &slot);
 }
 
 struct Root {
@@ -94,13 +104,18 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     if (m <= 0 || n <= 0) return GM_ERR_BAD_SHAPE;
     P.max_pivots = g.opt.max_pivots;
     P.refactor_period = g.opt.refactor_period;
+    const gm::WsLayout wr = gm::ws_layout(m, n, kSmemThreads, true);
     const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads);
     const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads);
+    const size_t smem_reg = wr.big_bytes + wr.small_bytes;
     const size_t smem_all = w1.big_bytes + w1.small_bytes;
+    const bool fits_reg = m <= 64 && smem_reg + 64 <= g.smem_optin;
+    const bool fits_smem = smem_all + 64 <= g.smem_optin;
+    const bool fits_small = w2.small_bytes + 64 <= g.smem_optin;
     int tier = g.opt.force_tier;
-    if (tier == 0) tier = smem_all + 64 <= g.smem_optin ? 1 : (w2.small_bytes + 64 <= g.smem_optin ? 2 : 3);
-    if (tier == 1 && smem_all + 64 > g.smem_optin) return GM_ERR_TOO_LARGE;
-    if (tier == 2 && w2.small_bytes + 64 > g.smem_optin) return GM_ERR_TOO_LARGE;
+    if (tier == 0) tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_small ? 3 : 4));
+    if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_small) || tier < 1 || tier > 4)
+        return GM_ERR_TOO_LARGE;
 
     int* queue = nullptr;
     CK(cudaMallocAsync(&queue, sizeof(int), stream));
@@ -109,12 +124,11 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     double* work = nullptr;
     int grid = 0, block = 0;
     size_t smem = 0;
-    if (tier == 1) {
+    if (tier == 1 || tier == 2) {
         block = kSmemThreads;
-        smem = smem_all;
+        smem = tier == 1 ? smem_reg : smem_all;
         int per_sm = 0;
-        // two kernels: up to 2 CTAs/SM (register cap 128) or many small ones
-        auto kern = simplex_wave_smem<kSmemThreads, 2>;
+        auto kern = tier == 1 ? simplex_wave_reg<kSmemThreads, 2> : simplex_wave_smem<kSmemThreads, 2>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
         if (per_sm < 1) per_sm = 1;
@@ -123,12 +137,12 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         kern<<<grid, block, smem, stream>>>(P);
     } else {
         block = kHbmThreads;
-        const size_t per_cta = tier == 2 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8);
+        const size_t per_cta = tier == 3 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8);
         grid = (int)std::min<long long>(P.count, (long long)g.sms);
         CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));
         P.work = work;
         P.work_stride = (long long)per_cta;
-        if (tier == 2) {
+        if (tier == 3) {
             smem = w2.small_bytes;
             auto kern = simplex_wave_hbm<kHbmThreads>;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

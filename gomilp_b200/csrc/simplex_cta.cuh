@@ -69,39 +69,54 @@ struct BatchParams {
 // index lists, reduction scratch: O(m+n)). Tier 1 keeps both in shared memory, tier 2 keeps the big
 // part in HBM and the small part in shared memory, tier 3 keeps both in HBM.
 struct WsLayout {
-    int ldw, ldb, nn1;
+    int ldw, ldb, nn1, wrows, vlen;
     size_t W, Bi;         // offsets in doubles inside the big part
     size_t big_doubles;
     size_t xb, cb, y, al, mv, bv, prow, art, t1, t2, cn, r, red;  // offsets in doubles inside the small part
     size_t small_doubles;
-    size_t basic, nonbasic, inb, redi, ipiv;  // offsets in ints, after the small doubles
+    size_t basic, nonbasic, inb, redi, ipiv, cperm;  // offsets in ints, after the small doubles
     size_t n_ints;
     size_t big_bytes, small_bytes;
 };
 
+// reg = the register-resident tier (m <= 64, 256 threads): Bi lives in registers, the "Bi" slot of the
+// workspace becomes a 64 x 68 staging tile, W gets a row stride = 4 (mod 16) and rows padded to a
+// multiple of 4, and every m-vector is padded to 64 entries (see SolverT<true>).
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline WsLayout ws_layout(int m, int n, int T) {
+inline WsLayout ws_layout(int m, int n, int T, bool reg = false) {
     WsLayout w;
-    w.ldw = (n + 1) | 1;
-    w.ldb = m | 1;
+    if (reg) {
+        int ld = n + 1;
+        while ((ld & 15) != 4) ++ld;
+        w.ldw = ld;
+        w.ldb = 68;
+        w.wrows = (m + 3) & ~3;
+        w.vlen = 64;
+    } else {
+        w.ldw = (n + 1) | 1;
+        w.ldb = m | 1;
+        w.wrows = m;
+        w.vlen = m;
+    }
     w.nn1 = (n + 1 - m) > 1 ? (n + 1 - m) : 1;
     size_t o = 0;
-    w.W = o; o += (size_t)m * w.ldw;
-    w.Bi = o; o += (size_t)m * w.ldb;
+    w.W = o; o += (size_t)w.wrows * w.ldw;
+    w.Bi = o; o += reg ? (size_t)64 * 68 : (size_t)m * w.ldb;
     w.big_doubles = o;
     o = 0;
-    w.xb = o; o += m;
-    w.cb = o; o += m;
-    w.y = o; o += m;
-    w.al = o; o += m;
-    w.mv = o; o += m;
-    w.bv = o; o += m;
-    w.prow = o; o += m;
-    w.art = o; o += m;
-    w.t1 = o; o += m;
-    w.t2 = o; o += m;
+    const size_t v = (size_t)w.vlen;
+    w.xb = o; o += v;
+    w.cb = o; o += v;
+    w.y = o; o += v;
+    w.al = o; o += v;
+    w.mv = o; o += v;
+    w.bv = o; o += v;
+    w.prow = o; o += v;
+    w.art = o; o += v;
+    w.t1 = o; o += v;
+    w.t2 = o; o += v;
     w.cn = o; o += w.nn1;
     w.r = o; o += w.nn1;
     w.red = o; o += T;
@@ -112,6 +127,7 @@ inline WsLayout ws_layout(int m, int n, int T) {
     w.inb = q; q += n + 1;
     w.redi = q; q += T;
     w.ipiv = q; q += m;
+    w.cperm = q; q += 64;
     w.n_ints = q;
     w.big_bytes = w.big_doubles * sizeof(double);
     w.small_bytes = w.small_doubles * sizeof(double) + ((w.n_ints * sizeof(int) + 7) / 8) * 8;
@@ -123,7 +139,8 @@ struct MinLoc {
     int i;
 };
 
-struct Solver {
+template <bool REG>
+struct SolverT {
     // problem
     int m, n, m0, n0, L, lda;
     const double *c0, *A0, *b0;
@@ -131,9 +148,13 @@ struct Solver {
     const double *bsign, *brhs;
     // workspace
     double *W, *Bi, *xb, *cb, *y, *al, *mv, *bv, *prow, *art, *t1, *t2, *cn, *r, *red;
-    int *basic, *nonbasic, *inb, *redi, *ipiv;
+    int *basic, *nonbasic, *inb, *redi, *ipiv, *cperm;
     int ldw, ldb;
+    // REG tier: thread t = (row = t >> 2, q = t & 3) keeps Bi[row][4*jj + q], jj = 0..15, in registers
+    double breg[REG ? 16 : 1];
     int ncols, nn;  // current width of W and number of non-basic columns
+    int wrows, vlen;  // rows of W incl. zero padding; length of the m-vectors incl. zero padding
+    double anorm_w;  // inf-norm of the initial basis, scale of the polish residual test
     // counters (uniform across the CTA)
     int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
     int max_pivots, refactor_period;
@@ -346,9 +367,9 @@ struct Solver {
                 if (!inb[j]) nonbasic[k++] = j;
         }
         gm_sync();
-        for_each_2d(m, ncols, [&](int i, int p) {
+        for_each_2d(wrows, ncols, [&](int i, int p) {
             const int v = p < m ? basic[p] : nonbasic[p - m];
-            W[(size_t)i * ldw + p] = (v == n) ? art[i] : src_a(i, v);
+            W[(size_t)i * ldw + p] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
         });
         for (int p = t; p < m; p += T) {
             const int v = basic[p];
@@ -361,11 +382,108 @@ struct Solver {
         gm_sync();
     }
 
+    // =================================================================================================
+    // Basis-inverse storage. Generic tiers: Bi is an m x ldb array (shared memory or HBM). REG tier:
+    // registers, with the Bi slot of the workspace used as a 64 x 68 staging tile.
+    // =================================================================================================
+    GM_DEV double reg_sel(int jj) const {
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < (REG ? 16 : 1); ++u)
+            if (u == jj) v = breg[u];
+        return v;
+    }
+
+    GM_DEV void reg_dump() {  // staging tile <- registers (ends with a barrier)
+        const int t = gm_tid(), row = t >> 2, q = t & 3;
+#pragma unroll
+        for (int jj = 0; jj < (REG ? 16 : 1); ++jj) Bi[row * ldb + 4 * jj + q] = breg[jj];
+        gm_sync();
+    }
+
+    // Bi[i][j] = f(i, j) for i, j < m
+    template <class F>
+    GM_DEV void bi_fill(F f) {
+        if constexpr (REG) {
+            const int t = gm_tid(), row = t >> 2, q = t & 3;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int col = 4 * jj + q;
+                breg[jj] = (row < m && col < m) ? f(row, col) : (row == col ? 1.0 : 0.0);
+            }
+        } else {
+            for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = f(i, j); });
+            gm_sync();
+        }
+    }
+
+    // out[i] = sum_j Bi[i][j] * a[j]; `a` is a workspace vector (REG: zero beyond m, up to 64 entries)
+    GM_DEV void bi_mul(double* out, const double* a) {
+        if constexpr (REG) {
+            const int t = gm_tid(), row = t >> 2, q = t & 3;
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+                a0 += breg[jj] * a[4 * jj + q];
+                a1 += breg[jj + 1] * a[4 * jj + 4 + q];
+            }
+            double acc = a0 + a1;
+            acc += gm_shfl_xor(acc, 1);
+            acc += gm_shfl_xor(acc, 2);
+            if (q == 0 && row < m) out[row] = acc;
+            gm_sync();
+        } else {
+            matvec_n(out, nullptr, 1.0, Bi, ldb, m, m, a);
+        }
+    }
+
+    // out[j] = sum_i x[i] * Bi[i][j]
+    GM_DEV void bi_mul_t(double* out, const double* x) {
+        if constexpr (REG) reg_dump();
+        matvec_t(out, nullptr, 1.0, Bi, ldb, m, m, x);
+    }
+
+    // product-form update: row l := row l / al[l]; row i -= al[i] * (new row l). `al` in the workspace.
+    GM_DEV void bi_update(int l, const double* alv) {
+        const int t = gm_tid(), T = gm_nthreads();
+        if constexpr (REG) {
+            const int row = t >> 2, q = t & 3;
+            const double f = row < m ? alv[row] : 0.0;
+            if (row == l) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) prow[4 * jj + q] = breg[jj] / f;
+            }
+            gm_sync();
+            if (row == l) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) breg[jj] = prow[4 * jj + q];
+            } else if (f != 0.0) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) breg[jj] -= f * prow[4 * jj + q];
+            }
+            gm_sync();
+        } else {
+            const double ap = alv[l];
+            for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] / ap;
+            gm_sync();
+            for_each_2d(m, m, [&](int i, int j) {
+                if (i == l) {
+                    Bi[(size_t)i * ldb + j] = prow[j];
+                } else {
+                    const double f = alv[i];
+                    if (f != 0.0) Bi[(size_t)i * ldb + j] -= f * prow[j];
+                }
+            });
+            gm_sync();
+        }
+    }
+
     // ---- Bi <- inverse of W[:, 0:m] by in-place Gauss-Jordan with partial (row) pivoting -----------
     // Stands in for the LU behind every VecDense.SolveVec (mat/solve.go:110-140, lu.go:63-84,293-325).
     // Returns 0, or 1 when a pivot is exactly zero / non-finite or cond_inf > 1e16 (the two conditions
     // under which LU.Solve reports mat.Condition, lu.go:301,321). *cond1 = ||B||_1 * ||B^-1||_1.
     GM_DEV int invert_basis(double* cond1) {
+        if constexpr (REG) return invert_basis_reg(cond1);
         const int t = gm_tid(), T = gm_nthreads();
         ninv++;
         for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = W[(size_t)i * ldw + j]; });
@@ -445,15 +563,184 @@ struct Solver {
         return 0;
     }
 
+    // The same Gauss-Jordan inversion with the matrix in registers: two barriers per elimination step,
+    // pivot row and displaced row exchanged through prow / t1, column interchanges undone in one pass
+    // through the staging tile.
+    GM_DEV int invert_basis_reg(double* cond1) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int row = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5;
+        ninv++;
+        bi_fill([&](int i, int j) { return W[(size_t)i * ldw + j]; });
+        double rs = 0;
+#pragma unroll
+        for (int jj = 0; jj < (REG ? 16 : 1); ++jj) rs += fabs(breg[jj]);
+        rs += gm_shfl_xor(rs, 1);
+        rs += gm_shfl_xor(rs, 2);
+        if (row >= m) rs = 0.0;
+        const double anorm_inf = block_max(T, [&](int k) { return k == t ? rs : 0.0; });
+        const double anorm_1 = block_max(m, [&](int j) {
+            double s = 0;
+            for (int i = 0; i < m; ++i) s += fabs(W[(size_t)i * ldw + j]);
+            return s;
+        });
+        int singular = 0;
+        for (int k = 0; k < m; ++k) {
+            const int kq = k & 3;
+            const double sel = reg_sel(k >> 2);
+            double key = (q == kq && row >= k && row < m) ? fabs(sel) : -1.0;
+            if (key != key) key = INFINITY;
+            int idx = row;
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double ok = gm_shfl_xor(key, d);
+                const int oi = gm_shfl_xor(idx, d);
+                if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+            }
+            if (lane == 0) { red[warp] = key; redi[warp] = idx; }
+            gm_sync();
+            key = red[0];
+            idx = redi[0];
+            for (int w = 1; w < nw; ++w) {
+                const double ok = red[w];
+                const int oi = redi[w];
+                if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+            }
+            if (!(key > 0.0) || key == INFINITY) { singular = 1; break; }
+            const int p = idx;
+            double f = gm_shfl_idx(sel, (lane & ~3) | kq);  // my row's entry in column k
+            if (row == p) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
+                    const int col = 4 * jj + q;
+                    prow[col] = (col == k ? 1.0 : breg[jj]) / f;
+                }
+            }
+            if (row == k && p != k) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) t1[4 * jj + q] = breg[jj];
+            }
+            if (t == 0) ipiv[k] = p;
+            gm_sync();
+            if (row == k) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] = prow[4 * jj + q];
+            } else {
+                if (row == p) {  // adopt the displaced row k
+#pragma unroll
+                    for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] = t1[4 * jj + q];
+                    f = t1[k];
+                }
+                if (f != 0.0) {
+#pragma unroll
+                    for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
+                        const int col = 4 * jj + q;
+                        const double base = (col == k) ? 0.0 : breg[jj];
+                        breg[jj] = base - f * prow[col];
+                    }
+                }
+            }
+        }
+        gm_sync();
+        if (singular) {
+            *cond1 = INFINITY;
+            return 1;
+        }
+        // (PA)^-1 P : the column interchanges compose into one permutation, applied through the tile
+        reg_dump();
+        if (t == 0) {
+            for (int j = 0; j < 64; ++j) cperm[j] = j;
+            for (int k = m - 1; k >= 0; --k) {
+                const int p = ipiv[k];
+                const int a = cperm[k];
+                cperm[k] = cperm[p];
+                cperm[p] = a;
+            }
+        }
+        gm_sync();
+#pragma unroll
+        for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] = Bi[row * ldb + cperm[4 * jj + q]];
+        double is = 0;
+#pragma unroll
+        for (int jj = 0; jj < (REG ? 16 : 1); ++jj) is += fabs(breg[jj]);
+        is += gm_shfl_xor(is, 1);
+        is += gm_shfl_xor(is, 2);
+        if (row >= m) is = 0.0;
+        const double inorm_inf = block_max(T, [&](int k) { return k == t ? is : 0.0; });
+        const double inorm_1 = block_max(m, [&](int j) {  // column sums are permutation invariant
+            double s = 0;
+            for (int i = 0; i < m; ++i) s += fabs(Bi[i * ldb + j]);
+            return s;
+        });
+        *cond1 = anorm_1 * inorm_1;
+        const double cond_inf = anorm_inf * inorm_inf;
+        if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
+        return 0;
+    }
+
     // xb = Bi b ; y = Bi^T cb
     GM_DEV void recompute_xb_y() {
-        matvec_n(xb, nullptr, 1.0, Bi, ldb, m, m, bv);
-        matvec_t(y, nullptr, 1.0, Bi, ldb, m, m, cb);
+        bi_mul(xb, bv);
+        bi_mul_t(y, cb);
     }
 
     GM_DEV bool xb_feasible() {  // initializeFromBasic's positivity test, simplex.go:459-468
         const int bad = block_min_int(m, [&](int i) { return xb[i] < -GM_INIT_POS_TOL ? i : INT_MAX; });
         return bad == INT_MAX;
+    }
+
+    // ---- "polish": what a fresh factorisation would give, at O(m^2) ----------------------------------
+    // One or two steps of iterative refinement of xb (B xb = b) and y (B^T y = cb) against the basic
+    // columns kept in W[:, 0:m], using the product-form inverse as the approximate solver. Falls back
+    // to a full re-inversion when the inverse has drifted too far for refinement to contract.
+    GM_DEV int polish() {
+        const int t = gm_tid(), T = gm_nthreads();
+        const double an = block_max(m, [&](int i) {
+            double s = 0;
+            for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
+            return s;
+        });
+        const double a1 = block_max(m, [&](int j) {
+            double s = 0;
+            for (int i = 0; i < m; ++i) s += fabs(W[(size_t)i * ldw + j]);
+            return s;
+        });
+        // The product-form inverse contracts the error by ||I - Bi B|| per step (1e-10 or better unless
+        // it has drifted badly), so two steps land on the accuracy of the residual evaluation itself,
+        // which is what a fresh LU solve achieves. A residual that starts large or does not collapse
+        // sends us to a full re-inversion.
+        for (int it = 0; it < 3; ++it) {
+            // t1 = b - B xb ; t2 = cb - B^T y
+            matvec_n(t1, bv, -1.0, W, ldw, m, m, xb);
+            matvec_t(t2, cb, -1.0, W, ldw, m, m, y);
+            const double rb = block_max(m, [&](int i) { return fabs(t1[i]); });
+            const double rc = block_max(m, [&](int i) { return fabs(t2[i]); });
+            const double sb = block_max(m, [&](int i) { return fabs(bv[i]); }) +
+                              an * block_max(m, [&](int i) { return fabs(xb[i]); }) + 1e-300;
+            const double sc = block_max(m, [&](int i) { return fabs(cb[i]); }) +
+                              block_max(nn, [&](int k) { return fabs(cn[k]); }) +
+                              a1 * block_max(m, [&](int i) { return fabs(y[i]); }) + 1e-300;
+#ifdef GM_DEBUG_EMU
+            if (t == 0) printf("polish it=%d rb=%g sb=%g rc=%g sc=%g\n", it, rb, sb, rc, sc);
+#endif
+            if (it == 2) {
+                if (rb <= 1e-13 * sb && rc <= 1e-13 * sc) return GM_OK;
+                break;
+            }
+            if (!(rb <= 1e-6 * sb) || !(rc <= 1e-6 * sc)) break;
+            bi_mul(al, t1);     // dx
+            bi_mul_t(mv, t2);   // dy
+            for (int i = t; i < m; i += T) {
+                xb[i] += al[i];
+                y[i] += mv[i];
+            }
+            gm_sync();
+        }
+#ifdef GM_DEBUG_EMU
+        if (t == 0) printf("polish -> reinversion at pivot %d\n", piv1 + piv2);
+#endif
+        double cond1;
+        if (invert_basis(&cond1)) return GM_ERR_CONDITION;
+        recompute_xb_y();
+        return GM_OK;
     }
 
     // ---- the last m columns taken as a permutation matrix (pure slack basis): Bi = B^T ---------------
@@ -491,15 +778,14 @@ struct Solver {
         gm_sync();
         build_w(n, false);
         // B[:,p] = e_row(p)  =>  B^-1 = B^T : Bi[p][row(p)] = 1, i.e. Bi[i][j] = (ipiv[j] == i)
-        for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = (ipiv[j] == i) ? 1.0 : 0.0; });
-        gm_sync();
+        bi_fill([&](int i, int j) { return (ipiv[j] == i) ? 1.0 : 0.0; });
         return true;
     }
 
     // ---- findLinearlyIndependent, simplex.go:611-637, with mat.Cond(.,1) of the QR factor ----------
-    // (matrix.go:284-322, qr.go:23-39: cond = ||R||_1 ||R^-1||_1). Q (m x k) lives in Bi, R^-1 in W.
-    // Orthogonalisation is classical Gram-Schmidt applied twice; R^-1 and both 1-norms are carried
-    // incrementally, so a candidate costs O(mk + k^2) instead of a fresh O(mk^2) QR.
+    // (matrix.go:284-322, qr.go:23-39: cond = ||R||_1 ||R^-1||_1). Q (m x k) lives in the Bi slot of the
+    // workspace, R^-1 in W. Orthogonalisation is classical Gram-Schmidt applied twice; R^-1 and both
+    // 1-norms are carried incrementally, so a candidate costs O(mk + k^2) instead of a fresh O(mk^2) QR.
     GM_DEV int scan_basis() {
         const int t = gm_tid(), T = gm_nthreads();
         scan_fb = 1;
@@ -541,6 +827,9 @@ struct Solver {
             ++k;
             gm_sync();
         }
+        // the scan used the padded vectors as scratch: restore their zero tails (REG tier invariant)
+        for (int i = m + t; i < vlen; i += T) { t1[i] = 0.0; t2[i] = 0.0; prow[i] = 0.0; mv[i] = 0.0; }
+        gm_sync();
         return k;
     }
 
@@ -550,7 +839,7 @@ struct Solver {
         // a_e is column m+e of W; stage it contiguously (t1) for the row-dot
         for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + m + e];
         gm_sync();
-        matvec_n(al, nullptr, 1.0, Bi, ldb, m, m, t1);
+        bi_mul(al, t1);
         // d = -al, |d| < dRoundTol -> 0 ; Min(d) >= 0 -> unbounded ; move_i = xb_i / |d_i| for d_i < 0
         for (int i = t; i < m; i += T) {
             double d = -al[i];
@@ -560,7 +849,6 @@ struct Solver {
         }
         gm_sync();
         const int anyneg = block_min_int(m, [&](int i) { return t2[i] < 0.0 ? i : INT_MAX; });
-        // NaN in d: floats.Min skips nothing special; treat a NaN-only column as "no negative"
         if (anyneg == INT_MAX) return GM_ERR_UNBOUNDED;
         return GM_OK;
     }
@@ -592,18 +880,9 @@ struct Solver {
     // ---- basis change: product-form update of Bi, xb, y; column swap in W (simplex.go:280-292) -------
     GM_DEV void pivot(int l, int e, double re) {
         const int t = gm_tid(), T = gm_nthreads();
-        const double ap = al[l];
-        const double theta = xb[l] / ap;
-        for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] / ap;
+        const double theta = xb[l] / al[l];
         gm_sync();
-        for_each_2d(m, m, [&](int i, int j) {
-            if (i == l) {
-                Bi[(size_t)i * ldb + j] = prow[j];
-            } else {
-                const double f = al[i];
-                if (f != 0.0) Bi[(size_t)i * ldb + j] -= f * prow[j];
-            }
-        });
+        bi_update(l, al);  // leaves the new row l in prow
         for (int i = t; i < m; i += T) {
             xb[i] = (i == l) ? theta : xb[i] - al[i] * theta;
             y[i] += re * prow[i];
@@ -633,6 +912,7 @@ struct Solver {
     // Returns GM_OK (optimal), GM_ERR_UNBOUNDED (caller returns -Inf / nil) or a "break" status
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
+        if constexpr (REG) return main_loop_reg(tol, phase, fresh);
         const int t = gm_tid(), T = gm_nthreads();
         int since = 0;
         for (;;) {
@@ -640,13 +920,11 @@ struct Solver {
             // r = cn - an^T y  (:236-243)
             matvec_t(r, cn, -1.0, W + m, ldw, m, nn, y);
             MinLoc rl = block_argmin(nn, [&](int k) { return r[k]; });
-            if (rl.v >= -tol || rl.v != rl.v) {  // :247-250 (NaN compares false in Go too: falls through there;
-                                                  // here a NaN-only r ends the loop through the polish below)
-                if (!fresh) {  // polish: confirm optimality with freshly inverted factors
-                    const int rc = refactor();
+            if (rl.v >= -tol || rl.v != rl.v) {  // :247-250 (a NaN-only r also ends the loop, via the polish)
+                if (!fresh) {  // confirm optimality with fresh-quality xb and y
+                    const int rc = polish();
                     if (rc != GM_OK) return rc;
                     fresh = true;
-                    since = 0;
                     continue;
                 }
                 return GM_OK;
@@ -678,6 +956,159 @@ struct Solver {
         }
     }
 
+    // REG tier main loop: one simplex iteration = four barriers.
+    //   pricing   thread (k = t>>2, q) sums rows i = q (mod 4) of non-basic column k, quad-reduces, then the
+    //             (value, position) argmin crosses the warp by shuffles and the CTA through `red`
+    //   FTRAN     thread (row, q) dots its 16 registers with column e of W read in place, quad-reduces
+    //   ratio     same shuffle argmin over rows
+    //   update    the quad of row l publishes the scaled pivot row, everybody does 16 FMAs in registers
+    GM_DEV int main_loop_reg(double tol, int phase, bool fresh) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int row = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5;
+        const int nq = wrows >> 2;
+        int since = 0;
+        for (;;) {
+            if (piv1 + piv2 >= max_pivots) return GM_ERR_ITERATION_LIMIT;
+            // ---- pricing: r = cn - an^T y, first minimum (:236-250)
+            double bestv = INFINITY;
+            int besti = INT_MAX;
+            for (int k0 = 0; k0 < nn; k0 += 64) {
+                const int k = k0 + row;
+                const bool valid = k < nn;
+                const double* wc = W + m + (valid ? k : 0) + q * ldw;
+                const double* yq = y + q;
+                double a0 = 0, a1 = 0;
+#pragma unroll
+                for (int ii = 0; ii < 16; ii += 2) {
+                    if (ii < nq) a0 += yq[4 * ii] * wc[(4 * ii) * ldw];
+                    if (ii + 1 < nq) a1 += yq[4 * ii + 4] * wc[(4 * ii + 4) * ldw];
+                }
+                double acc = a0 + a1;
+                acc += gm_shfl_xor(acc, 1);
+                acc += gm_shfl_xor(acc, 2);
+                if (valid) {
+                    const double rk = cn[k] - acc;
+                    if (q == 0) r[k] = fabs(rk) < GM_R_ROUND_TOL ? 0.0 : rk;  // rounded copy for Bland (:252-256)
+                    if (rk == rk && (besti == INT_MAX || rk < bestv)) { bestv = rk; besti = k; }
+                }
+            }
+            for (int d = 4; d <= 16; d <<= 1) {
+                const double ov = gm_shfl_xor(bestv, d);
+                const int oi = gm_shfl_xor(besti, d);
+                if (oi != INT_MAX && (besti == INT_MAX || ov < bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+            }
+            if (lane == 0) { red[warp] = bestv; redi[warp] = besti; }
+            gm_sync();  // (1)
+            bestv = red[0];
+            besti = redi[0];
+            for (int w = 1; w < nw; ++w) {
+                const double ov = red[w];
+                const int oi = redi[w];
+                if (oi != INT_MAX && (besti == INT_MAX || ov < bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+            }
+            if (besti == INT_MAX || bestv >= -tol) {
+                if (!fresh) {
+                    gm_sync();
+                    const int rc = polish();
+                    if (rc != GM_OK) return rc;
+                    fresh = true;
+                    continue;
+                }
+                gm_sync();
+                return GM_OK;
+            }
+            int e = besti;
+            double re = bestv;
+            // ---- FTRAN + ratio test (computeMove :306-342, MinIdx(move) :268)
+            double alpha;
+            {
+                const double* wc = W + m + e + q * ldw;
+                double a0 = 0, a1 = 0;
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); jj += 2) {
+                    if (jj < nq) a0 += breg[jj] * wc[(4 * jj) * ldw];
+                    if (jj + 1 < nq) a1 += breg[jj + 1] * wc[(4 * jj + 4) * ldw];
+                }
+                alpha = a0 + a1;
+                alpha += gm_shfl_xor(alpha, 1);
+                alpha += gm_shfl_xor(alpha, 2);
+            }
+            double mvv = INFINITY;
+            int mi = INT_MAX;
+            if (row < m) {
+                double d = -alpha;
+                if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+                mvv = d < 0.0 ? xb[row] / fabs(d) : INFINITY;
+                if (mvv == mvv) mi = row;
+                if (q == 0) { al[row] = alpha; mv[row] = mvv; }
+            }
+            for (int d = 4; d <= 16; d <<= 1) {
+                const double ov = gm_shfl_xor(mvv, d);
+                const int oi = gm_shfl_xor(mi, d);
+                if (oi != INT_MAX && (mi == INT_MAX || ov < mvv || (ov == mvv && oi < mi))) { mvv = ov; mi = oi; }
+            }
+            if (lane == 0) { red[32 + warp] = mvv; redi[32 + warp] = mi; }
+            gm_sync();  // (2)
+            mvv = red[32];
+            mi = redi[32];
+            for (int w = 1; w < nw; ++w) {
+                const double ov = red[32 + w];
+                const int oi = redi[32 + w];
+                if (oi != INT_MAX && (mi == INT_MAX || ov < mvv || (ov == mvv && oi < mi))) { mvv = ov; mi = oi; }
+            }
+            if (mi == INT_MAX) mi = 0;
+            if (mvv == INFINITY) { gm_sync(); return GM_ERR_UNBOUNDED; }  // Min(d) >= 0 (:329-331)
+            int l = mi;
+            if (mvv <= 0.0) {  // :268-277
+                nbland++;
+                gm_sync();
+                const int rc = replace_bland(l, e);
+                if (rc != GM_OK) return rc;
+                re = r[e];
+                alpha = row < m ? al[row] : 0.0;
+            }
+            // ---- basis change (:280-292)
+            if (row == l) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) prow[4 * jj + q] = breg[jj] / alpha;
+                if (q == 0) red[64] = xb[l] / alpha;
+            }
+            gm_sync();  // (3)
+            const double theta = red[64];
+            if (row == l) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] = prow[4 * jj + q];
+            } else if (alpha != 0.0) {
+#pragma unroll
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] -= alpha * prow[4 * jj + q];
+            }
+            if (q == 0 && row < m) xb[row] = (row == l) ? theta : xb[row] - alpha * theta;
+            if (t < m) {
+                y[t] += re * prow[t];
+                const double a = W[(size_t)t * ldw + l];
+                W[(size_t)t * ldw + l] = W[(size_t)t * ldw + m + e];
+                W[(size_t)t * ldw + m + e] = a;
+            }
+            if (t == 0) {
+                const int v = basic[l];
+                basic[l] = nonbasic[e];
+                nonbasic[e] = v;
+                const double cc = cb[l];
+                cb[l] = cn[e];
+                cn[e] = cc;
+            }
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            gm_sync();  // (4)
+            if (++since >= refactor_period) {
+                const int rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+            }
+        }
+    }
+
     // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
     GM_DEV int find_initial_basic(bool& fresh) {
         const int t = gm_tid(), T = gm_nthreads();
@@ -699,11 +1130,12 @@ struct Solver {
             build_w(n, false);
             invert_basis(&cond1);  // a singular result falls into Phase I like initializeFromBasic's error does
         }
+        anorm_w = block_max(m, [&](int i) {
+            double s = 0;
+            for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
+            return s;
+        });
         recompute_xb_y();
-#ifdef GM_DEBUG_EMU
-        if (t == 0) { printf("basic:"); for (int p = 0; p < m; ++p) printf(" %d", basic[p]); printf(" xb:"); for (int p = 0; p < m; ++p) printf(" %g", xb[p]); printf(" scan=%d\n", scan_fb);
-          for (int i=0;i<m;++i){ for(int j=0;j<m;++j) printf(" %g", Bi[i*ldb+j]); printf("\n");} }
-#endif
         if (xb_feasible()) return GM_OK;
 
         // Phase I (:529-556)
@@ -719,18 +1151,9 @@ struct Solver {
         // B' = B with column j := art ; B^-1 art = xb - (1 - e_j)
         for (int i = t; i < m; i += T) al[i] = xb[i] - (i == j ? 0.0 : 1.0);
         gm_sync();
-        {
-            // product-form step on Bi only (the artificial enters position j)
-            const double ap = al[j];
-            for (int q = t; q < m; q += T) prow[q] = Bi[(size_t)j * ldb + q] / ap;
-            gm_sync();
-            for_each_2d(m, m, [&](int i, int q) {
-                if (i == j) Bi[(size_t)i * ldb + q] = prow[q];
-                else if (al[i] != 0.0) Bi[(size_t)i * ldb + q] -= al[i] * prow[q];
-            });
-            if (t == 0) basic[j] = n;
-            gm_sync();
-        }
+        bi_update(j, al);  // the artificial enters position j
+        if (t == 0) basic[j] = n;
+        gm_sync();
         build_w(n + 1, true);
         recompute_xb_y();
         fresh = false;
@@ -747,7 +1170,7 @@ struct Solver {
             if (rc == GM_ERR_ITERATION_LIMIT || rc == GM_PANIC_INITIAL_BASIC) return rc;
             return GM_ERR_PHASE1_WRAPPED + rc;  // :557-559
         }
-        fresh = true;  // main_loop returns optimal only right after a refactor
+        fresh = true;  // main_loop returns optimal only right after a polish
         const int added = block_min_int(m, [&](int p) { return basic[p] == n ? p : INT_MAX; });
         const double xart = added == INT_MAX ? 0.0 : xb[added];
         if (fabs(xart) > GM_PHASE1_ZERO_TOL) return GM_ERR_INFEASIBLE;  // :563-565
@@ -764,7 +1187,7 @@ struct Solver {
                 nrepair++;
                 for (int i = t; i < m; i += T) t1[i] = src_a(i, v);
                 gm_sync();
-                matvec_n(al, nullptr, 1.0, Bi, ldb, m, m, t1);
+                bi_mul(al, t1);
                 const double amax = block_max(m, [&](int q) { return fabs(al[q]); });
                 const double ap = al[added];
                 if (!(fabs(ap) > 1e-9 * fmax(1.0, amax))) continue;  // swapped basis (near-)singular
@@ -774,12 +1197,7 @@ struct Solver {
                     return nx < -GM_INIT_POS_TOL ? i : INT_MAX;
                 });
                 if (bad != INT_MAX) continue;
-                for (int q = t; q < m; q += T) prow[q] = Bi[(size_t)added * ldb + q] / ap;
-                gm_sync();
-                for_each_2d(m, m, [&](int i, int q) {
-                    if (i == added) Bi[(size_t)i * ldb + q] = prow[q];
-                    else if (al[i] != 0.0) Bi[(size_t)i * ldb + q] -= al[i] * prow[q];
-                });
+                bi_update(added, al);
                 for (int i = t; i < m; i += T) xb[i] = (i == added) ? theta : xb[i] - al[i] * theta;
                 if (t == 0) basic[added] = v;
                 gm_sync();
@@ -789,7 +1207,7 @@ struct Solver {
             if (!done) return GM_ERR_INFEASIBLE;
         }
         build_w(n, false);  // Phase II lists: basis positions kept, non-basic ascending again (:174-197)
-        matvec_t(y, nullptr, 1.0, Bi, ldb, m, m, cb);
+        bi_mul_t(y, cb);
         return GM_OK;
     }
 
@@ -797,11 +1215,17 @@ struct Solver {
     GM_DEV void solve(const BatchParams& P, int lp) {
         const int t = gm_tid(), T = gm_nthreads();
         piv1 = piv2 = nbland = ninv = used_p1 = scan_fb = nrepair = 0;
+        anorm_w = 0.0;
         int status = GM_OK;
         double optF = NAN;
         bool have_x = false, have_basis = false;
 
-        for (int i = t; i < m; i += T) bv[i] = src_b(i);
+        // every padded vector starts as zeros (REG tier reads up to 64 entries)
+        for (int i = t; i < vlen; i += T) {
+            xb[i] = 0.0; cb[i] = 0.0; y[i] = 0.0; al[i] = 0.0; mv[i] = 0.0; prow[i] = 0.0; art[i] = 0.0;
+            t1[i] = 0.0; t2[i] = 0.0;
+            bv[i] = i < m ? src_b(i) : 0.0;
+        }
         gm_sync();
         status = verify_inputs();
         if (status != GM_OK) {
@@ -816,7 +1240,7 @@ struct Solver {
             if (invert_basis(&c1)) {
                 status = GM_ERR_SINGULAR;
             } else {
-                matvec_n(xb, nullptr, 1.0, Bi, ldb, m, m, bv);
+                bi_mul(xb, bv);
                 const int neg = block_min_int(m, [&](int i) { return xb[i] < 0.0 ? i : INT_MAX; });
                 if (neg != INT_MAX) status = GM_ERR_INFEASIBLE;
                 else {
@@ -845,6 +1269,11 @@ struct Solver {
                         double c1;
                         if (invert_basis(&c1)) status = GM_PANIC_INITIAL_BASIC;
                         else {
+                            anorm_w = block_max(m, [&](int i) {
+                                double s = 0;
+                                for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
+                                return s;
+                            });
                             recompute_xb_y();
                             if (!xb_feasible()) status = GM_PANIC_INITIAL_BASIC;
                         }
@@ -903,14 +1332,15 @@ struct Solver {
         bvar = P.bvar ? P.bvar + (size_t)lp * L : nullptr;
         bsign = P.bsign ? P.bsign + (size_t)lp * L : nullptr;
         brhs = P.brhs ? P.brhs + (size_t)lp * L : nullptr;
-        const WsLayout w = ws_layout(m, n, gm_nthreads());
-        ldw = w.ldw; ldb = w.ldb;
+        const WsLayout w = ws_layout(m, n, gm_nthreads(), REG);
+        ldw = w.ldw; ldb = w.ldb; wrows = w.wrows; vlen = w.vlen;
         W = big + w.W; Bi = big + w.Bi;
         xb = small + w.xb; cb = small + w.cb; y = small + w.y; al = small + w.al;
         mv = small + w.mv; bv = small + w.bv; prow = small + w.prow; art = small + w.art; t1 = small + w.t1;
         t2 = small + w.t2; cn = small + w.cn; r = small + w.r; red = small + w.red;
         int* iw = reinterpret_cast<int*>(small + w.small_doubles);
         basic = iw + w.basic; nonbasic = iw + w.nonbasic; inb = iw + w.inb; redi = iw + w.redi; ipiv = iw + w.ipiv;
+        cperm = iw + w.cperm;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
         refactor_period = P.refactor_period > 0 ? P.refactor_period : 100;
         ncols = n; nn = n - m;
@@ -918,8 +1348,9 @@ struct Solver {
 };
 
 // Persistent CTA: pulls LP indices from a global counter until the batch is exhausted.
+template <bool REG>
 GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */) {
-    Solver s;
+    SolverT<REG> s;
     for (;;) {
         if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
         gm_sync();

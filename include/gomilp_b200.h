@@ -40,7 +40,8 @@ typedef struct gm_timing {
     int64_t lps;        /* LP relaxations solved */
     int64_t launches;   /* kernel launches */
     int64_t smem_bytes; /* dynamic shared memory per CTA (0: HBM-resident tier) */
-    int32_t tier;       /* 1 = shared-memory resident, 2 = HBM resident */
+    int32_t tier;       /* 1 = basis inverse in registers + W in shared memory (m <= 64), 2 = all in shared memory,
+                           3 = W / inverse in HBM + vectors in shared memory, 4 = all in HBM */
     int32_t grid, block;
 } gm_timing;
 int gm_last_timing(gm_timing* out);
@@ -49,7 +50,7 @@ int gm_last_timing(gm_timing* out);
 typedef struct gm_options {
     int32_t max_pivots;      /* safety cap per LP; the reference has none. default 50*(m+n)+1000 */
     int32_t refactor_period; /* pivots between rebuilds of the basis inverse. default 100 */
-    int32_t force_tier;      /* 0 auto, 1 shared memory, 2 HBM workspace */
+    int32_t force_tier;      /* 0 auto, else the gm_timing.tier to force (GM_ERR_TOO_LARGE if it does not fit) */
     int32_t reserved;
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */

@@ -181,6 +181,11 @@ inline double gm_shfl_down(double v, int d) { return gm_shfl_down_t(v, d); }
 inline int gm_shfl_down(int v, int d) { return gm_shfl_down_t(v, d); }
 inline double gm_shfl_xor(double v, int d) { return gm_shfl_xor_t(v, d); }
 inline int gm_shfl_xor(int v, int d) { return gm_shfl_xor_t(v, d); }
+inline double gm_shfl_idx(double v, int src_lane) {
+    emu::Cta* c = emu::current();
+    int src = (c->cur & ~31) | (src_lane & 31);
+    return emu::shfl_generic(v, src < c->T, src);
+}
 inline int gm_any(int pred) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = pred ? 1 : 0;

@@ -14,7 +14,7 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
                       long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
                       const double* bsign, const double* brhs, const long long* initial_basic, double tol,
                       int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
-                      int x_len, long long* basis, int* stats, int T, int shuffle_order) {
+                      int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg) {
     gm::BatchParams P;
     std::memset(&P, 0, sizeof(P));
     P.c = c; P.A = A; P.b = b;
@@ -27,11 +27,13 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
     P.basis = basis; P.stats = stats;
     int queue = 0;
     P.queue = &queue;
-    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T);
+    if (reg && (T != 256 || m0 + L > 64)) return -2;
+    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T, reg != 0);
     std::vector<double> big(w.big_doubles + 8, 0.0), small(w.small_bytes / 8 + 8, 0.0);
     int slot = 0;
     try {
-        emu::run_cta(T, [&]() { gm::cta_main(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
+        if (reg) emu::run_cta(T, [&]() { gm::cta_main<true>(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
+        else emu::run_cta(T, [&]() { gm::cta_main<false>(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return -1;
@@ -51,10 +53,11 @@ struct EmuRoot { std::vector<double> c, A, b; int m0, n0; };
 std::map<gm_root_t, EmuRoot> g_roots;
 gm_root_t g_next = 1;
 int g_T = 64;
+int g_reg = 0;
 }  // namespace
 
 extern "C" {
-void emu_set_threads(int T) { g_T = T; }
+void emu_set_threads(int T, int reg) { g_T = T; g_reg = reg; }
 int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
                    gm_root_t* out) {
     EmuRoot r;
@@ -77,7 +80,8 @@ int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar,
     EmuRoot& r = it->second;
     int rc = emu_simplex_batch((int)nodes, r.c.data(), r.A.data(), r.b.data(), 0, 0, 0, r.n0, r.m0, r.n0, (int)L, bvar,
                                bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0,
-                               reinterpret_cast<long long*>(basis), stats, g_T, 0);
+                               reinterpret_cast<long long*>(basis), stats, g_T, 0,
+                               (g_reg && r.m0 + (int)L <= 64) ? 1 : 0);
     return rc == 0 ? GM_OK : GM_ERR_CUDA;
 }
 }  // extern "C"

@@ -45,7 +45,7 @@ def _p(a):
 
 
 def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_basic=None, T=64,
-                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False):
+                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False, reg=False):
     """Batch of LPs through the emulated kernel.
 
     Plain batch: A [count,m,n], c [count,n], b [count,m]. Wave mode (shared_root=True): one root
@@ -79,9 +79,10 @@ def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_ba
                                  C.c_longlong(bs), C.c_int(n0), C.c_int(m0), C.c_int(n0), C.c_int(L), _p(bvar),
                                  _p(bsign), _p(brhs), _p(ib), C.c_double(tol), C.c_int(max_pivots),
                                  C.c_int(refactor_period), _p(status), _p(optF), _p(x), C.c_longlong(x_len),
-                                 C.c_int(x_len), _p(basis), _p(stats), C.c_int(T), C.c_int(int(shuffle_order)))
+                                 C.c_int(x_len), _p(basis), _p(stats), C.c_int(256 if reg else T), C.c_int(int(shuffle_order)),
+                                 C.c_int(int(reg)))
     if rc != 0:
-        raise RuntimeError("CTA emulator reported barrier divergence")
+        raise RuntimeError("CTA emulator: barrier divergence" if rc == -1 else "CTA emulator: bad tier request")
     return {"status": status, "optF": optF, "x": x, "basis": basis, "stats": stats}
 
 
@@ -96,10 +97,10 @@ _WCB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double
 
 
 def milp_solve(c, A=None, b=None, G=None, h=None, integrality=None, heuristic=0, mode=0, node_limit=0,
-               time_limit_s=0.0, T=64):
+               time_limit_s=0.0, T=64, reg=False):
     """The product's gm_milp_solve (bnb_host.cpp) with every wave solved by the emulated kernel."""
     L = lib()
-    L.emu_set_threads(C.c_int(T))
+    L.emu_set_threads(C.c_int(256 if reg else T), C.c_int(int(reg)))
     c = np.ascontiguousarray(c, dtype=np.float64)
     nvar = c.shape[0]
     meq = 0 if A is None else np.asarray(A).shape[0]

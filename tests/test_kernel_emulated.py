@@ -19,26 +19,27 @@ def _close(a, b, tol=1e-9):
     return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(1.0, np.abs(np.asarray(b)))) <= tol
 
 
-@pytest.mark.parametrize("T", [32, 64])
-def test_emulated_kernel_matches_oracle_on_feasible_lps(T):
+@pytest.mark.parametrize("T,reg", [(32, False), (64, False), (256, True)])
+def test_emulated_kernel_matches_oracle_on_feasible_lps(T, reg):
     rng = np.random.default_rng(11 + T)
     for (m, n, k) in [(1, 3, 4), (3, 7, 6), (6, 13, 6), (12, 25, 4), (20, 40, 2)]:
         c, A, b = feasible_bounded_lp(rng, m, n, k)
-        g = E.simplex_batch(c, A, b, T=T, shuffle_order=True)
+        g = E.simplex_batch(c, A, b, T=T, shuffle_order=True, reg=reg)
         o = oracle.simplex_batch(c, A, b)
         assert (g["status"] == o["status"]).all() and (o["status"] == S.GM_OK).all()
         assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
         assert np.max(np.abs(np.einsum("kij,kj->ki", A, g["x"]) - b)) < 1e-9
 
 
-def test_emulated_kernel_status_parity_on_raw_lps():
+@pytest.mark.parametrize("reg", [False, True])
+def test_emulated_kernel_status_parity_on_raw_lps(reg):
     rng = np.random.default_rng(5)
     agree = total = 0
     for trial in range(12):
         m = int(rng.integers(1, 9))
         n = int(rng.integers(m, 13))
         c, A, b = raw_lp(rng, m, n, 12, p_zero=0.4 if trial % 3 == 0 else 0.0)
-        g = E.simplex_batch(c, A, b, T=64)
+        g = E.simplex_batch(c, A, b, T=64, reg=reg)
         o = oracle.simplex_batch(c, A, b, max_pivots=10000)
         for i in range(12):
             total += 1
@@ -49,26 +50,28 @@ def test_emulated_kernel_status_parity_on_raw_lps():
     assert agree >= total - 1
 
 
-def test_emulated_kernel_square_tall_and_initial_basic():
+@pytest.mark.parametrize("reg", [False, True])
+def test_emulated_kernel_square_tall_and_initial_basic(reg):
     p = PINS["singular_16x14"]
-    g = E.simplex_batch(np.array([p["c"]], float), np.array([p["A"]], float), np.array([p["b"]], float), T=32)
+    g = E.simplex_batch(np.array([p["c"]], float), np.array([p["A"]], float), np.array([p["b"]], float), T=32, reg=reg)
     assert g["status"][0] == S.GM_ERR_SINGULAR
     A = np.array([[[2.0, 1.0], [1.0, 3.0]]])
-    g = E.simplex_batch(np.array([[1.0, 1.0]]), A, np.array([[3.0, 4.0]]), T=32)   # m == n, simplex.go:103-119
+    g = E.simplex_batch(np.array([[1.0, 1.0]]), A, np.array([[3.0, 4.0]]), T=32, reg=reg)   # m == n, simplex.go:103-119
     assert g["status"][0] == S.GM_OK and _close(g["x"][0], [1.0, 1.0]) and _close(g["optF"][0], 2.0)
-    g = E.simplex_batch(np.array([[1.0, 1.0]]), A, np.array([[-3.0, 4.0]]), T=32)
+    g = E.simplex_batch(np.array([[1.0, 1.0]]), A, np.array([[-3.0, 4.0]]), T=32, reg=reg)
     assert g["status"][0] == S.GM_ERR_INFEASIBLE
     # warm start from the optimal basis: zero pivots (simplex.go:147-160)
     rng = np.random.default_rng(3)
     c, A, b = feasible_bounded_lp(rng, 5, 11, 1)
     o = oracle.simplex(c[0], A[0], b[0])
-    g = E.simplex_batch(c, A, b, initial_basic=o.basis[None, :], T=32)
+    g = E.simplex_batch(c, A, b, initial_basic=o.basis[None, :], T=32, reg=reg)
     assert g["status"][0] == S.GM_OK and g["stats"][0, 0] + g["stats"][0, 1] == 0 and _close(g["x"][0], o.x)
     bad = np.array([[0, 0, 1, 2, 3]])  # repeated column: singular -> the reference panics
-    assert E.simplex_batch(c, A, b, initial_basic=bad, T=32)["status"][0] == S.GM_PANIC_INITIAL_BASIC
+    assert E.simplex_batch(c, A, b, initial_basic=bad, T=32, reg=reg)["status"][0] == S.GM_PANIC_INITIAL_BASIC
 
 
-def test_emulated_wave_matches_materialised_children():
+@pytest.mark.parametrize("reg", [False, True])
+def test_emulated_wave_matches_materialised_children(reg):
     """Branch rows synthesised on the fly == convertToEqualities materialised (subproblem.go:81-139)."""
     rng = np.random.default_rng(9)
     p = random_milp(rng, 5, 3)
@@ -78,7 +81,7 @@ def test_emulated_wave_matches_materialised_children():
     bvar = rng.integers(0, 5, size=(nodes, L)).astype(np.int32)
     bsign = rng.choice([-1.0, 1.0], size=(nodes, L))
     brhs = np.where(bsign > 0, rng.integers(0, 4, size=(nodes, L)), -rng.integers(1, 3, size=(nodes, L))).astype(float)
-    g = E.simplex_batch(c0, A0, b0, bvar=bvar, bsign=bsign, brhs=brhs, shared_root=True, T=64)
+    g = E.simplex_batch(c0, A0, b0, bvar=bvar, bsign=bsign, brhs=brhs, shared_root=True, T=64, reg=reg)
     for k in range(nodes):
         A = np.zeros((m0 + L, n0 + L))
         A[:m0, :n0] = A0
@@ -91,10 +94,11 @@ def test_emulated_wave_matches_materialised_children():
             assert _close(g["optF"][k], o.optF) and _close(g["x"][k], o.x[:n0])
 
 
+@pytest.mark.parametrize("reg", [False, True])
 @pytest.mark.parametrize("case", PINS["milp"], ids=[c["src"].split(" ")[0] for c in PINS["milp"]])
-def test_emulated_bnb_reproduces_reference_pins(case):
-    r = E.milp_solve(case["c"], case["A"], case["b"], case["G"], case["h"], case["integrality"], node_limit=400,
-                     T=32)
+def test_emulated_bnb_reproduces_reference_pins(case, reg):
+    r = E.milp_solve(case["c"], case["A"], case["b"], case["G"], case["h"], case["integrality"],
+                     node_limit=100 if reg else 400, T=32, reg=reg)
     assert r["rc"] == 0 and r["status"] == MILP_STATUS[case["want_status"]]
     if case["want_status"] == "OK":
         assert _close(r["x"], case["want_x"], 1e-12) and abs(r["z"] - case["want_z"]) <= 1e-12
