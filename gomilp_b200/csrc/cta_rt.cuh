@@ -20,6 +20,8 @@ GM_DEV int gm_shfl_down(int v, int d) { return __shfl_down_sync(0xffffffffu, v, 
 GM_DEV double gm_shfl_xor(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 GM_DEV int gm_shfl_xor(int v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 GM_DEV double gm_shfl_idx(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+GM_DEV void gm_syncwarp() { __syncwarp(); }
+GM_DEV int gm_shfl_idx(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 GM_DEV int gm_any(int pred) { return __any_sync(0xffffffffu, pred); }
 GM_DEV int gm_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 GM_DEV double gm_ldg(const double* p) { return __ldg(p); }

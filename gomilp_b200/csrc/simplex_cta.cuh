@@ -92,7 +92,7 @@ inline WsLayout ws_layout(int m, int n, int T, bool reg = false) {
         while ((ld & 15) != 4) ++ld;
         w.ldw = ld;
         w.ldb = 68;
-        w.wrows = (m + 3) & ~3;
+        w.wrows = 64;
         w.vlen = 64;
     } else {
         w.ldw = (n + 1) | 1;
@@ -956,19 +956,47 @@ struct SolverT {
         }
     }
 
-    // REG tier main loop: one simplex iteration = four barriers.
-    //   pricing   thread (k = t>>2, q) sums rows i = q (mod 4) of non-basic column k, quad-reduces, then the
-    //             (value, position) argmin crosses the warp by shuffles and the CTA through `red`
-    //   FTRAN     thread (row, q) dots its 16 registers with column e of W read in place, quad-reduces
-    //   ratio     same shuffle argmin over rows
-    //   update    the quad of row l publishes the scaled pivot row, everybody does 16 FMAs in registers
+    // REG tier main loop: one simplex iteration = three barriers, state in registers.
+    //   pricing   thread (k = t>>2, q) sums rows i = q (mod 4) of non-basic column k against its register copy
+    //             of y, quad-reduces; the (value, position) argmin crosses the warp by shuffles and the CTA
+    //             through `red`                                                                   barrier 1
+    //   FTRAN     thread (row, q) dots its 16 registers of Bi with column e of W read in place, quad-reduces;
+    //   ratio     same shuffle argmin over rows                                                   barrier 2
+    //   publish   the quad of row l writes the scaled pivot row (and theta)                       barrier 3
+    //   update    16 FMAs on Bi, 16 on y, xb, all in registers; the warp that prices column e swaps it in W
+    // xb (per row) and y (per q) are spilled to the workspace only around the rare generic paths.
     GM_DEV int main_loop_reg(double tol, int phase, bool fresh) {
         const int t = gm_tid(), T = gm_nthreads();
         const int row = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5;
-        const int nq = wrows >> 2;
         int since = 0;
+        double yreg[REG ? 16 : 1];
+        double xbr;
+        auto load_state = [&]() {
+#pragma unroll
+            for (int ii = 0; ii < (REG ? 16 : 1); ++ii) yreg[ii] = y[4 * ii + q];
+            xbr = row < m ? xb[row] : 0.0;
+        };
+        auto store_state = [&]() {
+            if (row == 0) {
+#pragma unroll
+                for (int ii = 0; ii < (REG ? 16 : 1); ++ii) y[4 * ii + q] = yreg[ii];
+            }
+            if (q == 0 && row < m) xb[row] = xbr;
+            gm_sync();
+        };
+        // cross-warp stage of a (value, position) first-minimum: every warp re-reduces the nw partials
+        auto cross = [&](const double* rv, const int* ri, double& v, int& i) {
+            v = rv[lane & (nw - 1)];
+            i = ri[lane & (nw - 1)];
+            for (int d = 1; d < nw; d <<= 1) {
+                const double ov = gm_shfl_xor(v, d);
+                const int oi = gm_shfl_xor(i, d);
+                if (oi != INT_MAX && (i == INT_MAX || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
+            }
+        };
+        load_state();
         for (;;) {
-            if (piv1 + piv2 >= max_pivots) return GM_ERR_ITERATION_LIMIT;
+            if (piv1 + piv2 >= max_pivots) { store_state(); return GM_ERR_ITERATION_LIMIT; }
             // ---- pricing: r = cn - an^T y, first minimum (:236-250)
             double bestv = INFINITY;
             int besti = INT_MAX;
@@ -976,14 +1004,15 @@ struct SolverT {
                 const int k = k0 + row;
                 const bool valid = k < nn;
                 const double* wc = W + m + (valid ? k : 0) + q * ldw;
-                const double* yq = y + q;
-                double a0 = 0, a1 = 0;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-                for (int ii = 0; ii < 16; ii += 2) {
-                    if (ii < nq) a0 += yq[4 * ii] * wc[(4 * ii) * ldw];
-                    if (ii + 1 < nq) a1 += yq[4 * ii + 4] * wc[(4 * ii + 4) * ldw];
+                for (int ii = 0; ii < (REG ? 16 : 1); ii += 4) {
+                    a0 += yreg[ii] * wc[(4 * ii) * ldw];
+                    a1 += yreg[ii + 1] * wc[(4 * ii + 4) * ldw];
+                    a2 += yreg[ii + 2] * wc[(4 * ii + 8) * ldw];
+                    a3 += yreg[ii + 3] * wc[(4 * ii + 12) * ldw];
                 }
-                double acc = a0 + a1;
+                double acc = (a0 + a1) + (a2 + a3);
                 acc += gm_shfl_xor(acc, 1);
                 acc += gm_shfl_xor(acc, 2);
                 if (valid) {
@@ -999,22 +1028,16 @@ struct SolverT {
             }
             if (lane == 0) { red[warp] = bestv; redi[warp] = besti; }
             gm_sync();  // (1)
-            bestv = red[0];
-            besti = redi[0];
-            for (int w = 1; w < nw; ++w) {
-                const double ov = red[w];
-                const int oi = redi[w];
-                if (oi != INT_MAX && (besti == INT_MAX || ov < bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-            }
+            cross(red, redi, bestv, besti);
             if (besti == INT_MAX || bestv >= -tol) {
+                store_state();
                 if (!fresh) {
-                    gm_sync();
                     const int rc = polish();
                     if (rc != GM_OK) return rc;
                     fresh = true;
+                    load_state();
                     continue;
                 }
-                gm_sync();
                 return GM_OK;
             }
             int e = besti;
@@ -1023,13 +1046,15 @@ struct SolverT {
             double alpha;
             {
                 const double* wc = W + m + e + q * ldw;
-                double a0 = 0, a1 = 0;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-                for (int jj = 0; jj < (REG ? 16 : 1); jj += 2) {
-                    if (jj < nq) a0 += breg[jj] * wc[(4 * jj) * ldw];
-                    if (jj + 1 < nq) a1 += breg[jj + 1] * wc[(4 * jj + 4) * ldw];
+                for (int jj = 0; jj < (REG ? 16 : 1); jj += 4) {
+                    a0 += breg[jj] * wc[(4 * jj) * ldw];
+                    a1 += breg[jj + 1] * wc[(4 * jj + 4) * ldw];
+                    a2 += breg[jj + 2] * wc[(4 * jj + 8) * ldw];
+                    a3 += breg[jj + 3] * wc[(4 * jj + 12) * ldw];
                 }
-                alpha = a0 + a1;
+                alpha = (a0 + a1) + (a2 + a3);
                 alpha += gm_shfl_xor(alpha, 1);
                 alpha += gm_shfl_xor(alpha, 2);
             }
@@ -1038,9 +1063,8 @@ struct SolverT {
             if (row < m) {
                 double d = -alpha;
                 if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
-                mvv = d < 0.0 ? xb[row] / fabs(d) : INFINITY;
+                mvv = d < 0.0 ? xbr / fabs(d) : INFINITY;
                 if (mvv == mvv) mi = row;
-                if (q == 0) { al[row] = alpha; mv[row] = mvv; }
             }
             for (int d = 4; d <= 16; d <<= 1) {
                 const double ov = gm_shfl_xor(mvv, d);
@@ -1049,19 +1073,13 @@ struct SolverT {
             }
             if (lane == 0) { red[32 + warp] = mvv; redi[32 + warp] = mi; }
             gm_sync();  // (2)
-            mvv = red[32];
-            mi = redi[32];
-            for (int w = 1; w < nw; ++w) {
-                const double ov = red[32 + w];
-                const int oi = redi[32 + w];
-                if (oi != INT_MAX && (mi == INT_MAX || ov < mvv || (ov == mvv && oi < mi))) { mvv = ov; mi = oi; }
-            }
+            cross(red + 32, redi + 32, mvv, mi);
             if (mi == INT_MAX) mi = 0;
-            if (mvv == INFINITY) { gm_sync(); return GM_ERR_UNBOUNDED; }  // Min(d) >= 0 (:329-331)
+            if (mvv == INFINITY) { store_state(); return GM_ERR_UNBOUNDED; }  // Min(d) >= 0 (:329-331)
             int l = mi;
             if (mvv <= 0.0) {  // :268-277
                 nbland++;
-                gm_sync();
+                store_state();
                 const int rc = replace_bland(l, e);
                 if (rc != GM_OK) return rc;
                 re = r[e];
@@ -1069,42 +1087,49 @@ struct SolverT {
             }
             // ---- basis change (:280-292)
             if (row == l) {
+                const double inv = 1.0 / alpha;
 #pragma unroll
-                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) prow[4 * jj + q] = breg[jj] / alpha;
-                if (q == 0) red[64] = xb[l] / alpha;
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) prow[4 * jj + q] = breg[jj] * inv;
+                if (q == 0) red[64] = xbr * inv;
             }
             gm_sync();  // (3)
             const double theta = red[64];
-            if (row == l) {
+            {
+                const double f = row == l ? 0.0 : alpha;
 #pragma unroll
-                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] = prow[4 * jj + q];
-            } else if (alpha != 0.0) {
-#pragma unroll
-                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) breg[jj] -= alpha * prow[4 * jj + q];
+                for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
+                    const double pr = prow[4 * jj + q];
+                    breg[jj] = row == l ? pr : breg[jj] - f * pr;
+                    yreg[jj] += re * pr;
+                }
             }
-            if (q == 0 && row < m) xb[row] = (row == l) ? theta : xb[row] - alpha * theta;
-            if (t < m) {
-                y[t] += re * prow[t];
-                const double a = W[(size_t)t * ldw + l];
-                W[(size_t)t * ldw + l] = W[(size_t)t * ldw + m + e];
-                W[(size_t)t * ldw + m + e] = a;
-            }
-            if (t == 0) {
-                const int v = basic[l];
-                basic[l] = nonbasic[e];
-                nonbasic[e] = v;
-                const double cc = cb[l];
-                cb[l] = cn[e];
-                cn[e] = cc;
+            xbr = (row == l) ? theta : xbr - alpha * theta;
+            // column e of the non-basic part <-> column l of the basic part, done by the warp that prices e
+            if (warp == ((e & 63) >> 3)) {
+                for (int i = lane; i < m; i += 32) {
+                    const double a = W[(size_t)i * ldw + l];
+                    W[(size_t)i * ldw + l] = W[(size_t)i * ldw + m + e];
+                    W[(size_t)i * ldw + m + e] = a;
+                }
+                if (lane == 0) {
+                    const int v = basic[l];
+                    basic[l] = nonbasic[e];
+                    nonbasic[e] = v;
+                    const double cc = cb[l];
+                    cb[l] = cn[e];
+                    cn[e] = cc;
+                }
+                gm_syncwarp();
             }
             if (phase == 1) piv1++; else piv2++;
             fresh = false;
-            gm_sync();  // (4)
             if (++since >= refactor_period) {
+                store_state();
                 const int rc = refactor();
                 if (rc != GM_OK) return rc;
                 fresh = true;
                 since = 0;
+                load_state();
             }
         }
     }

@@ -186,6 +186,12 @@ inline double gm_shfl_idx(double v, int src_lane) {
     int src = (c->cur & ~31) | (src_lane & 31);
     return emu::shfl_generic(v, src < c->T, src);
 }
+inline int gm_shfl_idx(int v, int src_lane) {
+    emu::Cta* c = emu::current();
+    int src = (c->cur & ~31) | (src_lane & 31);
+    return emu::shfl_generic(v, src < c->T, src);
+}
+inline void gm_syncwarp() { emu::yield_as(emu::WAIT_WARP); }
 inline int gm_any(int pred) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = pred ? 1 : 0;
