@@ -20,6 +20,9 @@ GM_DEV int gm_shfl_down(int v, int d) { return __shfl_down_sync(0xffffffffu, v, 
 GM_DEV double gm_shfl_xor(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 GM_DEV int gm_shfl_xor(int v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
 GM_DEV double gm_shfl_idx(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+GM_DEV unsigned gm_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+GM_DEV int gm_warp_min_int(int v) { return __reduce_min_sync(0xffffffffu, v); }
+GM_DEV int gm_popc(unsigned v) { return __popc(v); }
 GM_DEV void gm_syncwarp() { __syncwarp(); }
 GM_DEV int gm_shfl_idx(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 GM_DEV int gm_any(int pred) { return __any_sync(0xffffffffu, pred); }

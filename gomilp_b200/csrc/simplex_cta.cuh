@@ -361,12 +361,26 @@ struct SolverT {
         gm_sync();
         for (int p = t; p < m; p += T) inb[basic[p]] = 1;
         gm_sync();
-        if (t == 0) {
-            int k = 0;
-            for (int j = 0; j < ncols; ++j)
-                if (!inb[j]) nonbasic[k++] = j;
+        {   // ascending list of the columns not in the basis: ballot ranks inside a warp, warp totals in redi
+            const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+            int base = 0;
+            for (int j0 = 0; j0 < ncols; j0 += T) {
+                const int j = j0 + t;
+                const int flag = (j < ncols) && !inb[j];
+                const unsigned bal = gm_ballot(flag);
+                if (lane == 0) redi[warp] = gm_popc(bal);
+                gm_sync();
+                int off = base, tot = 0;
+                for (int w = 0; w < nw; ++w) {
+                    const int c = redi[w];
+                    if (w < warp) off += c;
+                    tot += c;
+                }
+                if (flag) nonbasic[off + gm_popc(bal & ((1u << lane) - 1u))] = j;
+                base += tot;
+                gm_sync();
+            }
         }
-        gm_sync();
         for_each_2d(wrows, ncols, [&](int i, int p) {
             const int v = p < m ? basic[p] : nonbasic[p - m];
             W[(size_t)i * ldw + p] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
@@ -558,6 +572,7 @@ struct SolverT {
             return s;
         });
         *cond1 = anorm_1 * inorm_1;
+        anorm_w = fmax(anorm_1, anorm_inf);
         const double cond_inf = anorm_inf * inorm_inf;
         if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
         return 0;
@@ -589,29 +604,28 @@ struct SolverT {
             const double sel = reg_sel(k >> 2);
             double key = (q == kq && row >= k && row < m) ? fabs(sel) : -1.0;
             if (key != key) key = INFINITY;
-            int idx = row;
-            for (int d = 16; d >= 1; d >>= 1) {
-                const double ok = gm_shfl_xor(key, d);
-                const int oi = gm_shfl_xor(idx, d);
-                if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }
-            }
-            if (lane == 0) { red[warp] = key; redi[warp] = idx; }
+            // Idamax: first largest |.| in column k at or below the diagonal (dgetf2.go:43-45)
+            double km = key;
+            for (int d = 16; d >= 1; d >>= 1) km = fmax(km, gm_shfl_xor(km, d));
+            int idx = gm_warp_min_int(key == km ? row : INT_MAX);
+            if (lane == 0) { red[warp] = km; redi[warp] = idx; }
             gm_sync();
-            key = red[0];
-            idx = redi[0];
-            for (int w = 1; w < nw; ++w) {
-                const double ok = red[w];
-                const int oi = redi[w];
-                if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }
-            }
+            key = red[lane & (nw - 1)];
+            idx = redi[lane & (nw - 1)];
+            km = key;
+            for (int d = 1; d < nw; d <<= 1) km = fmax(km, gm_shfl_xor(km, d));
+            idx = gm_warp_min_int(key == km ? idx : INT_MAX);
+            key = km;
             if (!(key > 0.0) || key == INFINITY) { singular = 1; break; }
             const int p = idx;
             double f = gm_shfl_idx(sel, (lane & ~3) | kq);  // my row's entry in column k
             if (row == p) {
 #pragma unroll
+                const double inv = 1.0 / f;
+#pragma unroll
                 for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
                     const int col = 4 * jj + q;
-                    prow[col] = (col == k ? 1.0 : breg[jj]) / f;
+                    prow[col] = (col == k ? 1.0 : breg[jj]) * inv;
                 }
             }
             if (row == k && p != k) {
@@ -671,6 +685,7 @@ struct SolverT {
             return s;
         });
         *cond1 = anorm_1 * inorm_1;
+        anorm_w = fmax(anorm_1, anorm_inf);
         const double cond_inf = anorm_inf * inorm_inf;
         if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
         return 0;
@@ -693,39 +708,15 @@ struct SolverT {
     // to a full re-inversion when the inverse has drifted too far for refinement to contract.
     GM_DEV int polish() {
         const int t = gm_tid(), T = gm_nthreads();
-        const double an = block_max(m, [&](int i) {
-            double s = 0;
-            for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
-            return s;
-        });
-        const double a1 = block_max(m, [&](int j) {
-            double s = 0;
-            for (int i = 0; i < m; ++i) s += fabs(W[(size_t)i * ldw + j]);
-            return s;
-        });
-        // The product-form inverse contracts the error by ||I - Bi B|| per step (1e-10 or better unless
-        // it has drifted badly), so two steps land on the accuracy of the residual evaluation itself,
-        // which is what a fresh LU solve achieves. A residual that starts large or does not collapse
-        // sends us to a full re-inversion.
+        // The product-form inverse contracts the error by ||I - Bi B|| per step (1e-10 or better unless it
+        // has drifted badly), so two steps land on the accuracy of the residual evaluation itself, which
+        // is what a fresh LU solve achieves. A residual that does not collapse sends us to a full
+        // re-inversion.
         for (int it = 0; it < 3; ++it) {
             // t1 = b - B xb ; t2 = cb - B^T y
             matvec_n(t1, bv, -1.0, W, ldw, m, m, xb);
             matvec_t(t2, cb, -1.0, W, ldw, m, m, y);
-            const double rb = block_max(m, [&](int i) { return fabs(t1[i]); });
-            const double rc = block_max(m, [&](int i) { return fabs(t2[i]); });
-            const double sb = block_max(m, [&](int i) { return fabs(bv[i]); }) +
-                              an * block_max(m, [&](int i) { return fabs(xb[i]); }) + 1e-300;
-            const double sc = block_max(m, [&](int i) { return fabs(cb[i]); }) +
-                              block_max(nn, [&](int k) { return fabs(cn[k]); }) +
-                              a1 * block_max(m, [&](int i) { return fabs(y[i]); }) + 1e-300;
-#ifdef GM_DEBUG_EMU
-            if (t == 0) printf("polish it=%d rb=%g sb=%g rc=%g sc=%g\n", it, rb, sb, rc, sc);
-#endif
-            if (it == 2) {
-                if (rb <= 1e-13 * sb && rc <= 1e-13 * sc) return GM_OK;
-                break;
-            }
-            if (!(rb <= 1e-6 * sb) || !(rc <= 1e-6 * sc)) break;
+            if (it == 2) break;
             bi_mul(al, t1);     // dx
             bi_mul_t(mv, t2);   // dy
             for (int i = t; i < m; i += T) {
@@ -734,9 +725,13 @@ struct SolverT {
             }
             gm_sync();
         }
-#ifdef GM_DEBUG_EMU
-        if (t == 0) printf("polish -> reinversion at pivot %d\n", piv1 + piv2);
-#endif
+        const double rb = block_max(m, [&](int i) { return fabs(t1[i]); });
+        const double rc = block_max(m, [&](int i) { return fabs(t2[i]); });
+        const double sb = block_max(m, [&](int i) { return fabs(bv[i]) + anorm_w * fabs(xb[i]); }) + 1e-300;
+        const double sc = block_max(m > nn ? m : nn, [&](int i) {
+            return (i < m ? fabs(cb[i]) + anorm_w * fabs(y[i]) : 0.0) + (i < nn ? fabs(cn[i]) : 0.0);
+        }) + 1e-300;
+        if (rb <= 1e-13 * sb && rc <= 1e-13 * sc) return GM_OK;
         double cond1;
         if (invert_basis(&cond1)) return GM_ERR_CONDITION;
         recompute_xb_y();
@@ -762,6 +757,7 @@ struct SolverT {
                         ++cnt;
                         row = i;
                         if (a != 1.0) cnt = 99;
+                        if (cnt > 1) break;
                     }
                 }
             }
@@ -779,6 +775,7 @@ struct SolverT {
         build_w(n, false);
         // B[:,p] = e_row(p)  =>  B^-1 = B^T : Bi[p][row(p)] = 1, i.e. Bi[i][j] = (ipiv[j] == i)
         bi_fill([&](int i, int j) { return (ipiv[j] == i) ? 1.0 : 0.0; });
+        anorm_w = 1.0;
         return true;
     }
 
@@ -984,15 +981,22 @@ struct SolverT {
             if (q == 0 && row < m) xb[row] = xbr;
             gm_sync();
         };
-        // cross-warp stage of a (value, position) first-minimum: every warp re-reduces the nw partials
+        // first minimum of (value, position) over the CTA: values by fmin butterflies, the position by a
+        // warp-wide integer min over the lanes that hold the minimum (ties -> lowest position, like MinIdx).
+        // Invalid entries carry (+Inf, INT_MAX). Quads hold identical values, so the butterfly starts at 4.
+        auto warp_argmin = [&](double& v, int& i) {
+            double vm = v;
+            for (int d = 4; d <= 16; d <<= 1) vm = fmin(vm, gm_shfl_xor(vm, d));
+            i = gm_warp_min_int(v == vm ? i : INT_MAX);
+            v = vm;
+        };
         auto cross = [&](const double* rv, const int* ri, double& v, int& i) {
             v = rv[lane & (nw - 1)];
             i = ri[lane & (nw - 1)];
-            for (int d = 1; d < nw; d <<= 1) {
-                const double ov = gm_shfl_xor(v, d);
-                const int oi = gm_shfl_xor(i, d);
-                if (oi != INT_MAX && (i == INT_MAX || ov < v || (ov == v && oi < i))) { v = ov; i = oi; }
-            }
+            double vm = v;
+            for (int d = 1; d < nw; d <<= 1) vm = fmin(vm, gm_shfl_xor(vm, d));
+            i = gm_warp_min_int(v == vm ? i : INT_MAX);
+            v = vm;
         };
         load_state();
         for (;;) {
@@ -1021,11 +1025,8 @@ struct SolverT {
                     if (rk == rk && (besti == INT_MAX || rk < bestv)) { bestv = rk; besti = k; }
                 }
             }
-            for (int d = 4; d <= 16; d <<= 1) {
-                const double ov = gm_shfl_xor(bestv, d);
-                const int oi = gm_shfl_xor(besti, d);
-                if (oi != INT_MAX && (besti == INT_MAX || ov < bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-            }
+            if (besti == INT_MAX) bestv = INFINITY;
+            warp_argmin(bestv, besti);
             if (lane == 0) { red[warp] = bestv; redi[warp] = besti; }
             gm_sync();  // (1)
             cross(red, redi, bestv, besti);
@@ -1064,13 +1065,9 @@ struct SolverT {
                 double d = -alpha;
                 if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
                 mvv = d < 0.0 ? xbr / fabs(d) : INFINITY;
-                if (mvv == mvv) mi = row;
+                if (mvv == mvv) mi = row; else mvv = INFINITY;
             }
-            for (int d = 4; d <= 16; d <<= 1) {
-                const double ov = gm_shfl_xor(mvv, d);
-                const int oi = gm_shfl_xor(mi, d);
-                if (oi != INT_MAX && (mi == INT_MAX || ov < mvv || (ov == mvv && oi < mi))) { mvv = ov; mi = oi; }
-            }
+            warp_argmin(mvv, mi);
             if (lane == 0) { red[32 + warp] = mvv; redi[32 + warp] = mi; }
             gm_sync();  // (2)
             cross(red + 32, redi + 32, mvv, mi);
@@ -1155,11 +1152,6 @@ struct SolverT {
             build_w(n, false);
             invert_basis(&cond1);  // a singular result falls into Phase I like initializeFromBasic's error does
         }
-        anorm_w = block_max(m, [&](int i) {
-            double s = 0;
-            for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
-            return s;
-        });
         recompute_xb_y();
         if (xb_feasible()) return GM_OK;
 
@@ -1294,11 +1286,6 @@ struct SolverT {
                         double c1;
                         if (invert_basis(&c1)) status = GM_PANIC_INITIAL_BASIC;
                         else {
-                            anorm_w = block_max(m, [&](int i) {
-                                double s = 0;
-                                for (int j = 0; j < m; ++j) s += fabs(W[(size_t)i * ldw + j]);
-                                return s;
-                            });
                             recompute_xb_y();
                             if (!xb_feasible()) status = GM_PANIC_INITIAL_BASIC;
                         }
@@ -1347,16 +1334,10 @@ struct SolverT {
         gm_sync();
     }
 
-    // ---- binding of one work item to the workspace --------------------------------------------------
-    GM_DEV void bind(const BatchParams& P, int lp, double* big, double* small) {
+    // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
+    GM_DEV void bind_workspace(const BatchParams& P, double* big, double* small) {
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
-        c0 = P.c + (size_t)lp * P.c_stride;
-        A0 = P.A + (size_t)lp * P.A_stride;
-        b0 = P.b + (size_t)lp * P.b_stride;
-        bvar = P.bvar ? P.bvar + (size_t)lp * L : nullptr;
-        bsign = P.bsign ? P.bsign + (size_t)lp * L : nullptr;
-        brhs = P.brhs ? P.brhs + (size_t)lp * L : nullptr;
         const WsLayout w = ws_layout(m, n, gm_nthreads(), REG);
         ldw = w.ldw; ldb = w.ldb; wrows = w.wrows; vlen = w.vlen;
         W = big + w.W; Bi = big + w.Bi;
@@ -1368,6 +1349,14 @@ struct SolverT {
         cperm = iw + w.cperm;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
         refactor_period = P.refactor_period > 0 ? P.refactor_period : 100;
+    }
+    GM_DEV void bind_lp(const BatchParams& P, int lp) {
+        c0 = P.c + (size_t)lp * P.c_stride;
+        A0 = P.A + (size_t)lp * P.A_stride;
+        b0 = P.b + (size_t)lp * P.b_stride;
+        bvar = P.bvar ? P.bvar + (size_t)lp * L : nullptr;
+        bsign = P.bsign ? P.bsign + (size_t)lp * L : nullptr;
+        brhs = P.brhs ? P.brhs + (size_t)lp * L : nullptr;
         ncols = n; nn = n - m;
     }
 };
@@ -1376,13 +1365,14 @@ struct SolverT {
 template <bool REG>
 GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */) {
     SolverT<REG> s;
+    s.bind_workspace(P, big, small);
     for (;;) {
         if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
         gm_sync();
         const int lp = *slot;
         gm_sync();
         if (lp >= P.count) break;
-        s.bind(P, lp, big, small);
+        s.bind_lp(P, lp);
         s.solve(P, lp);
     }
 }

@@ -12,6 +12,7 @@
 #pragma once
 #include <ucontext.h>
 
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -191,6 +192,26 @@ inline int gm_shfl_idx(int v, int src_lane) {
     int src = (c->cur & ~31) | (src_lane & 31);
     return emu::shfl_generic(v, src < c->T, src);
 }
+inline unsigned gm_ballot(int pred) {
+    emu::Cta* c = emu::current();
+    c->vote[c->cur] = pred ? 1 : 0;
+    emu::yield_as(emu::WAIT_WARP);
+    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    unsigned r = 0;
+    for (int t = w0; t < w1; ++t) r |= (unsigned)c->vote[t] << (t - w0);
+    emu::yield_as(emu::WAIT_WARP);
+    return r;
+}
+inline int gm_warp_min_int(int v) {
+    emu::Cta* c = emu::current();
+    c->vote[c->cur] = v;
+    emu::yield_as(emu::WAIT_WARP);
+    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32), r = INT_MAX;
+    for (int t = w0; t < w1; ++t) r = std::min(r, c->vote[t]);
+    emu::yield_as(emu::WAIT_WARP);
+    return r;
+}
+inline int gm_popc(unsigned v) { return __builtin_popcount(v); }
 inline void gm_syncwarp() { emu::yield_as(emu::WAIT_WARP); }
 inline int gm_any(int pred) {
     emu::Cta* c = emu::current();
