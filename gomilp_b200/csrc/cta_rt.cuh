@@ -22,6 +22,10 @@ GM_DEV int gm_shfl_xor(int v, int d) { return __shfl_xor_sync(0xffffffffu, v, d)
 GM_DEV double gm_shfl_idx(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 GM_DEV unsigned gm_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
 GM_DEV int gm_warp_min_int(int v) { return __reduce_min_sync(0xffffffffu, v); }
+GM_DEV unsigned gm_warp_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+GM_DEV unsigned gm_warp_max_u32(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+GM_DEV unsigned long long gm_d2bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+GM_DEV double gm_bits2d(unsigned long long b) { return __longlong_as_double((long long)b); }
 GM_DEV int gm_popc(unsigned v) { return __popc(v); }
 GM_DEV void gm_syncwarp() { __syncwarp(); }
 GM_DEV int gm_shfl_idx(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }

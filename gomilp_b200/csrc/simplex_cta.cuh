@@ -23,6 +23,9 @@
 //                 column) and column extraction (thread per row) are both bank-conflict free.
 //   Bi  m x ldb   basis inverse, row-major, odd ldb.
 //   vectors       xb, cb, y (duals), al (B^-1 a_e), mv (ratios), bv (rhs), prow, art, t1, t2, cn, r.
+// Tier 1 (SolverT<true>) differs: Bi lives in registers and W keeps the ORIGINAL column order (column v of
+// W is column v of A, column n the artificial); the positional lists basic[] / nonbasic[] are the only
+// thing a pivot permutes, so no column ever moves.
 // All reductions that pick an index return the FIRST minimum (value, position) like floats.MinIdx.
 #pragma once
 #include <math.h>
@@ -154,7 +157,8 @@ struct SolverT {
     double breg[REG ? 16 : 1];
     int ncols, nn;  // current width of W and number of non-basic columns
     int wrows, vlen;  // rows of W incl. zero padding; length of the m-vectors incl. zero padding
-    double anorm_w;  // inf-norm of the initial basis, scale of the polish residual test
+    double anorm_w;  // norm of the basis at its last inversion, scale of the polish residual test
+    bool w_loaded;   // REG tier: W holds [A | art] in ORIGINAL column order for the current LP
     // counters (uniform across the CTA)
     int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
     int max_pivots, refactor_period;
@@ -381,10 +385,19 @@ struct SolverT {
                 gm_sync();
             }
         }
-        for_each_2d(wrows, ncols, [&](int i, int p) {
-            const int v = p < m ? basic[p] : nonbasic[p - m];
-            W[(size_t)i * ldw + p] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
-        });
+        if constexpr (REG) {
+            if (!w_loaded) {
+                for_each_2d(wrows, n, [&](int i, int v) { W[i * ldw + v] = i < m ? src_a(i, v) : 0.0; });
+                w_loaded = true;
+            }
+            if (phase1)
+                for (int i = t; i < wrows; i += T) W[i * ldw + n] = i < m ? art[i] : 0.0;
+        } else {
+            for_each_2d(wrows, ncols, [&](int i, int p) {
+                const int v = p < m ? basic[p] : nonbasic[p - m];
+                W[(size_t)i * ldw + p] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
+            });
+        }
         for (int p = t; p < m; p += T) {
             const int v = basic[p];
             cb[p] = phase1 ? (v == n ? 1.0 : 0.0) : src_c(v);
@@ -394,6 +407,45 @@ struct SolverT {
             cn[k] = phase1 ? (v == n ? 1.0 : 0.0) : src_c(v);
         }
         gm_sync();
+    }
+
+    // physical column of W that holds basis position p / non-basic position k
+    GM_DEV int wcol_b(int p) const { return REG ? basic[p] : p; }
+    GM_DEV int wcol_n(int k) const { return REG ? nonbasic[k] : m + k; }
+
+    // out[i] = base[i] + sgn * sum_p B[i][p] x[p]   (B = basic columns of W)
+    GM_DEV void basis_mul(double* out, const double* base, double sgn, const double* x) {
+        if constexpr (REG) {
+            const int t = gm_tid(), row = t >> 2, q = t & 3;
+            double a = 0;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int p = 4 * jj + q;
+                if (p < m) a += W[row * ldw + basic[p]] * x[p];
+            }
+            a += gm_shfl_xor(a, 1);
+            a += gm_shfl_xor(a, 2);
+            if (q == 0 && row < m) out[row] = base[row] + sgn * a;
+            gm_sync();
+        } else {
+            matvec_n(out, base, sgn, W, ldw, m, m, x);
+        }
+    }
+    // out[p] = base[p] + sgn * sum_i x[i] B[i][p]
+    GM_DEV void basis_mul_t(double* out, const double* base, double sgn, const double* x) {
+        if constexpr (REG) {
+            const int t = gm_tid(), p = t >> 2, q = t & 3;
+            const double* wc = W + (p < m ? basic[p] : 0) + q * ldw;
+            double a = 0;
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) a += x[4 * ii + q] * wc[(4 * ii) * ldw];
+            a += gm_shfl_xor(a, 1);
+            a += gm_shfl_xor(a, 2);
+            if (q == 0 && p < m) out[p] = base[p] + sgn * a;
+            gm_sync();
+        } else {
+            matvec_t(out, base, sgn, W, ldw, m, m, x);
+        }
     }
 
     // =================================================================================================
@@ -585,7 +637,7 @@ struct SolverT {
         const int t = gm_tid(), T = gm_nthreads();
         const int row = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5;
         ninv++;
-        bi_fill([&](int i, int j) { return W[(size_t)i * ldw + j]; });
+        bi_fill([&](int i, int j) { return W[i * ldw + basic[j]]; });
         double rs = 0;
 #pragma unroll
         for (int jj = 0; jj < (REG ? 16 : 1); ++jj) rs += fabs(breg[jj]);
@@ -595,7 +647,8 @@ struct SolverT {
         const double anorm_inf = block_max(T, [&](int k) { return k == t ? rs : 0.0; });
         const double anorm_1 = block_max(m, [&](int j) {
             double s = 0;
-            for (int i = 0; i < m; ++i) s += fabs(W[(size_t)i * ldw + j]);
+            const int cj = basic[j];
+            for (int i = 0; i < m; ++i) s += fabs(W[i * ldw + cj]);
             return s;
         });
         int singular = 0;
@@ -714,8 +767,8 @@ struct SolverT {
         // re-inversion.
         for (int it = 0; it < 3; ++it) {
             // t1 = b - B xb ; t2 = cb - B^T y
-            matvec_n(t1, bv, -1.0, W, ldw, m, m, xb);
-            matvec_t(t2, cb, -1.0, W, ldw, m, m, y);
+            basis_mul(t1, bv, -1.0, xb);
+            basis_mul_t(t2, cb, -1.0, y);
             if (it == 2) break;
             bi_mul(al, t1);     // dx
             bi_mul_t(mv, t2);   // dy
@@ -786,6 +839,7 @@ struct SolverT {
     GM_DEV int scan_basis() {
         const int t = gm_tid(), T = gm_nthreads();
         scan_fb = 1;
+        w_loaded = false;
         for_each_2d(m, m, [&](int i, int j) { W[(size_t)i * ldw + j] = 0.0; });
         gm_sync();
         int k = 0;
@@ -834,7 +888,10 @@ struct SolverT {
     GM_DEV int compute_move(int e) {
         const int t = gm_tid(), T = gm_nthreads();
         // a_e is column m+e of W; stage it contiguously (t1) for the row-dot
-        for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + m + e];
+        {
+            const int ce = wcol_n(e);
+            for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + ce];
+        }
         gm_sync();
         bi_mul(al, t1);
         // d = -al, |d| < dRoundTol -> 0 ; Min(d) >= 0 -> unbounded ; move_i = xb_i / |d_i| for d_i < 0
@@ -953,18 +1010,39 @@ struct SolverT {
         }
     }
 
-    // REG tier main loop: one simplex iteration = three barriers, state in registers.
-    //   pricing   thread (k = t>>2, q) sums rows i = q (mod 4) of non-basic column k against its register copy
-    //             of y, quad-reduces; the (value, position) argmin crosses the warp by shuffles and the CTA
-    //             through `red`                                                                   barrier 1
-    //   FTRAN     thread (row, q) dots its 16 registers of Bi with column e of W read in place, quad-reduces;
-    //   ratio     same shuffle argmin over rows                                                   barrier 2
-    //   publish   the quad of row l writes the scaled pivot row (and theta)                       barrier 3
-    //   update    16 FMAs on Bi, 16 on y, xb, all in registers; the warp that prices column e swaps it in W
+    // order-preserving map double -> uint64 (-0.0 canonicalised by the caller)
+    GM_DEV static unsigned long long ord_key(double v) {
+        const unsigned long long u = gm_d2bits(v);
+        return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    }
+    GM_DEV static double ord_val(unsigned long long k) {
+        return gm_bits2d((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k);
+    }
+    // Exact first minimum of (value, position) over a warp with three integer REDUX ops: min of the high
+    // word of the ordered key, min of the low word among the lanes that match, min position among the
+    // lanes that hold the minimum (ties -> lowest position, like floats.MinIdx). Invalid lanes carry
+    // (+Inf, INT_MAX); NaN never reaches here.
+    GM_DEV static void warp_argmin(double& v, int& i) {
+        const unsigned long long kx = ord_key(v + 0.0);
+        const unsigned hi = (unsigned)(kx >> 32), lo = (unsigned)kx;
+        const unsigned mh = gm_warp_min_u32(hi);
+        const unsigned ml = gm_warp_min_u32(hi == mh ? lo : 0xffffffffu);
+        i = gm_warp_min_int((hi == mh && lo == ml) ? i : INT_MAX);
+        v = ord_val(((unsigned long long)mh << 32) | ml);
+    }
+
+    // REG tier main loop: one simplex iteration = three barriers, state in registers, nothing moves in W.
+    //   pricing   thread (k = t>>2, q) sums rows i = q (mod 4) of column nonbasic[k] against its register copy
+    //             of y, quad-reduces; first-minimum by REDUX inside the warp, through `red` across warps  barrier 1
+    //   FTRAN     thread (row, q) dots its 16 registers of Bi with column nonbasic[e] read in place;
+    //   ratio     same first-minimum over rows                                                          barrier 2
+    //   publish   the quad of row l writes the scaled pivot row (and theta)                              barrier 3
+    //   update    16 FMAs on Bi, 16 on y, xb, all in registers; one lane swaps the two list entries
     // xb (per row) and y (per q) are spilled to the workspace only around the rare generic paths.
     GM_DEV int main_loop_reg(double tol, int phase, bool fresh) {
         const int t = gm_tid(), T = gm_nthreads();
         const int row = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5;
+        const int s4 = 4 * ldw;
         int since = 0;
         double yreg[REG ? 16 : 1];
         double xbr;
@@ -981,23 +1059,6 @@ struct SolverT {
             if (q == 0 && row < m) xb[row] = xbr;
             gm_sync();
         };
-        // first minimum of (value, position) over the CTA: values by fmin butterflies, the position by a
-        // warp-wide integer min over the lanes that hold the minimum (ties -> lowest position, like MinIdx).
-        // Invalid entries carry (+Inf, INT_MAX). Quads hold identical values, so the butterfly starts at 4.
-        auto warp_argmin = [&](double& v, int& i) {
-            double vm = v;
-            for (int d = 4; d <= 16; d <<= 1) vm = fmin(vm, gm_shfl_xor(vm, d));
-            i = gm_warp_min_int(v == vm ? i : INT_MAX);
-            v = vm;
-        };
-        auto cross = [&](const double* rv, const int* ri, double& v, int& i) {
-            v = rv[lane & (nw - 1)];
-            i = ri[lane & (nw - 1)];
-            double vm = v;
-            for (int d = 1; d < nw; d <<= 1) vm = fmin(vm, gm_shfl_xor(vm, d));
-            i = gm_warp_min_int(v == vm ? i : INT_MAX);
-            v = vm;
-        };
         load_state();
         for (;;) {
             if (piv1 + piv2 >= max_pivots) { store_state(); return GM_ERR_ITERATION_LIMIT; }
@@ -1007,14 +1068,14 @@ struct SolverT {
             for (int k0 = 0; k0 < nn; k0 += 64) {
                 const int k = k0 + row;
                 const bool valid = k < nn;
-                const double* wc = W + m + (valid ? k : 0) + q * ldw;
+                const double* wc = W + (valid ? nonbasic[k] : 0) + q * ldw;
                 double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
                 for (int ii = 0; ii < (REG ? 16 : 1); ii += 4) {
-                    a0 += yreg[ii] * wc[(4 * ii) * ldw];
-                    a1 += yreg[ii + 1] * wc[(4 * ii + 4) * ldw];
-                    a2 += yreg[ii + 2] * wc[(4 * ii + 8) * ldw];
-                    a3 += yreg[ii + 3] * wc[(4 * ii + 12) * ldw];
+                    a0 += yreg[ii] * wc[ii * s4];
+                    a1 += yreg[ii + 1] * wc[(ii + 1) * s4];
+                    a2 += yreg[ii + 2] * wc[(ii + 2) * s4];
+                    a3 += yreg[ii + 3] * wc[(ii + 3) * s4];
                 }
                 double acc = (a0 + a1) + (a2 + a3);
                 acc += gm_shfl_xor(acc, 1);
@@ -1029,7 +1090,9 @@ struct SolverT {
             warp_argmin(bestv, besti);
             if (lane == 0) { red[warp] = bestv; redi[warp] = besti; }
             gm_sync();  // (1)
-            cross(red, redi, bestv, besti);
+            bestv = red[lane & (nw - 1)];
+            besti = redi[lane & (nw - 1)];
+            warp_argmin(bestv, besti);
             if (besti == INT_MAX || bestv >= -tol) {
                 store_state();
                 if (!fresh) {
@@ -1046,14 +1109,14 @@ struct SolverT {
             // ---- FTRAN + ratio test (computeMove :306-342, MinIdx(move) :268)
             double alpha;
             {
-                const double* wc = W + m + e + q * ldw;
+                const double* wc = W + nonbasic[e] + q * ldw;
                 double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
                 for (int jj = 0; jj < (REG ? 16 : 1); jj += 4) {
-                    a0 += breg[jj] * wc[(4 * jj) * ldw];
-                    a1 += breg[jj + 1] * wc[(4 * jj + 4) * ldw];
-                    a2 += breg[jj + 2] * wc[(4 * jj + 8) * ldw];
-                    a3 += breg[jj + 3] * wc[(4 * jj + 12) * ldw];
+                    a0 += breg[jj] * wc[jj * s4];
+                    a1 += breg[jj + 1] * wc[(jj + 1) * s4];
+                    a2 += breg[jj + 2] * wc[(jj + 2) * s4];
+                    a3 += breg[jj + 3] * wc[(jj + 3) * s4];
                 }
                 alpha = (a0 + a1) + (a2 + a3);
                 alpha += gm_shfl_xor(alpha, 1);
@@ -1070,12 +1133,15 @@ struct SolverT {
             warp_argmin(mvv, mi);
             if (lane == 0) { red[32 + warp] = mvv; redi[32 + warp] = mi; }
             gm_sync();  // (2)
-            cross(red + 32, redi + 32, mvv, mi);
+            mvv = red[32 + (lane & (nw - 1))];
+            mi = redi[32 + (lane & (nw - 1))];
+            warp_argmin(mvv, mi);
             if (mi == INT_MAX) mi = 0;
             if (mvv == INFINITY) { store_state(); return GM_ERR_UNBOUNDED; }  // Min(d) >= 0 (:329-331)
             int l = mi;
             if (mvv <= 0.0) {  // :268-277
                 nbland++;
+                if (q == 0 && row < m) { al[row] = alpha; }
                 store_state();
                 const int rc = replace_bland(l, e);
                 if (rc != GM_OK) return rc;
@@ -1092,22 +1158,18 @@ struct SolverT {
             gm_sync();  // (3)
             const double theta = red[64];
             {
-                const double f = row == l ? 0.0 : alpha;
+                // row l itself: breg - (alpha - 1) * (breg / alpha) = breg / alpha, so one FMA form serves every row
+                const double f = row == l ? alpha - 1.0 : alpha;
 #pragma unroll
                 for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
                     const double pr = prow[4 * jj + q];
-                    breg[jj] = row == l ? pr : breg[jj] - f * pr;
+                    breg[jj] -= f * pr;
                     yreg[jj] += re * pr;
                 }
             }
             xbr = (row == l) ? theta : xbr - alpha * theta;
-            // column e of the non-basic part <-> column l of the basic part, done by the warp that prices e
+            // the two list entries and costs swap; the warp that prices position e does it (no barrier needed)
             if (warp == ((e & 63) >> 3)) {
-                for (int i = lane; i < m; i += 32) {
-                    const double a = W[(size_t)i * ldw + l];
-                    W[(size_t)i * ldw + l] = W[(size_t)i * ldw + m + e];
-                    W[(size_t)i * ldw + m + e] = a;
-                }
                 if (lane == 0) {
                     const int v = basic[l];
                     basic[l] = nonbasic[e];
@@ -1164,7 +1226,7 @@ struct SolverT {
         gm_sync();
         if (t == 0) t1[j] = 0.0;
         gm_sync();
-        matvec_n(art, bv, -1.0, W, ldw, m, m, t1);
+        basis_mul(art, bv, -1.0, t1);
         // B' = B with column j := art ; B^-1 art = xb - (1 - e_j)
         for (int i = t; i < m; i += T) al[i] = xb[i] - (i == j ? 0.0 : 1.0);
         gm_sync();
@@ -1233,6 +1295,7 @@ struct SolverT {
         const int t = gm_tid(), T = gm_nthreads();
         piv1 = piv2 = nbland = ninv = used_p1 = scan_fb = nrepair = 0;
         anorm_w = 0.0;
+        w_loaded = false;
         int status = GM_OK;
         double optF = NAN;
         bool have_x = false, have_basis = false;

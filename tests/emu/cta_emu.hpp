@@ -211,6 +211,36 @@ inline int gm_warp_min_int(int v) {
     emu::yield_as(emu::WAIT_WARP);
     return r;
 }
+inline unsigned gm_warp_min_u32(unsigned v) {
+    emu::Cta* c = emu::current();
+    c->vote[c->cur] = (int)v;
+    emu::yield_as(emu::WAIT_WARP);
+    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    unsigned r = 0xffffffffu;
+    for (int t = w0; t < w1; ++t) r = std::min(r, (unsigned)c->vote[t]);
+    emu::yield_as(emu::WAIT_WARP);
+    return r;
+}
+inline unsigned gm_warp_max_u32(unsigned v) {
+    emu::Cta* c = emu::current();
+    c->vote[c->cur] = (int)v;
+    emu::yield_as(emu::WAIT_WARP);
+    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    unsigned r = 0;
+    for (int t = w0; t < w1; ++t) r = std::max(r, (unsigned)c->vote[t]);
+    emu::yield_as(emu::WAIT_WARP);
+    return r;
+}
+inline unsigned long long gm_d2bits(double v) {
+    unsigned long long b;
+    std::memcpy(&b, &v, 8);
+    return b;
+}
+inline double gm_bits2d(unsigned long long b) {
+    double v;
+    std::memcpy(&v, &b, 8);
+    return v;
+}
 inline int gm_popc(unsigned v) { return __builtin_popcount(v); }
 inline void gm_syncwarp() { emu::yield_as(emu::WAIT_WARP); }
 inline int gm_any(int pred) {
