@@ -354,6 +354,89 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
     return GM_OK;
 }
 
+// Large host batches: the batch is cut in chunks; chunk k+1 crosses PCIe on the copy stream while chunk k is
+// being solved, and consecutive chunks are launched on alternating compute streams so that the tail of
+// one launch overlaps the head of the next. Same results as one launch (LPs are independent).
+static int run_host_batch_pipelined(gm::BatchParams P, const double* h_c, const double* h_A, const double* h_b,
+                                    int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats,
+                                    int chunks) {
+    const int64_t count = P.count, m = P.m0, n = P.n0;
+    cudaStream_t cs = nullptr, ks[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev(3 * chunks + 2, nullptr);
+    auto cleanup = [&]() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (cs) cudaStreamDestroy(cs);
+        for (auto& k : ks) if (k) cudaStreamDestroy(k);
+    };
+#define CKP(call)                                                 \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return fail(e_, #call); } \
+    } while (0)
+    CKP(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CKP(cudaStreamCreateWithFlags(&ks[0], cudaStreamNonBlocking));
+    CKP(cudaStreamCreateWithFlags(&ks[1], cudaStreamNonBlocking));
+    for (auto& e : ev) CKP(cudaEventCreate(&e));
+    double *dc = nullptr, *dA = nullptr, *db = nullptr, *dF = nullptr, *dX = nullptr;
+    int32_t *dst = nullptr, *dS = nullptr;
+    long long* dB = nullptr;
+    CKP(cudaMallocAsync(&dc, sizeof(double) * count * n, cs));
+    CKP(cudaMallocAsync(&dA, sizeof(double) * count * m * n, cs));
+    CKP(cudaMallocAsync(&db, sizeof(double) * count * m, cs));
+    CKP(cudaMallocAsync(&dF, sizeof(double) * count, cs));
+    CKP(cudaMallocAsync(&dX, sizeof(double) * count * n, cs));
+    CKP(cudaMallocAsync(&dst, sizeof(int32_t) * count, cs));
+    if (basis) CKP(cudaMallocAsync(&dB, sizeof(long long) * count * m, cs));
+    if (stats) CKP(cudaMallocAsync(&dS, sizeof(int32_t) * count * 8, cs));
+    CKP(cudaEventRecord(ev[3 * chunks], cs));  // allocations done, start of the transfer clock
+    t_timing = gm_timing{};
+    const int64_t per = (count + chunks - 1) / chunks;
+    int rc = GM_OK;
+    for (int k = 0; k < chunks && rc == GM_OK; ++k) {
+        const int64_t off = k * per, cnt = std::min<int64_t>(per, count - off);
+        if (cnt <= 0) break;
+        CKP(cudaMemcpyAsync(dc + off * n, h_c + off * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+        CKP(cudaMemcpyAsync(dA + off * m * n, h_A + off * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
+        CKP(cudaMemcpyAsync(db + off * m, h_b + off * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
+        CKP(cudaEventRecord(ev[3 * k], cs));
+        cudaStream_t st = ks[k & 1];
+        CKP(cudaStreamWaitEvent(st, ev[3 * chunks], 0));
+        CKP(cudaStreamWaitEvent(st, ev[3 * k], 0));
+        gm::BatchParams Q = P;
+        Q.c = dc + off * n; Q.A = dA + off * m * n; Q.b = db + off * m; Q.lda = (int)n;
+        Q.count = (int)cnt;
+        Q.status = dst + off; Q.optF = dF + off; Q.x = dX + off * n; Q.x_stride = n;
+        Q.basis = basis ? dB + off * m : nullptr;
+        Q.stats = stats ? dS + off * 8 : nullptr;
+        rc = launch_wave(Q, st, ev[3 * k + 1], ev[3 * k + 2], &t_timing);
+        if (rc != GM_OK) break;
+        CKP(cudaMemcpyAsync(status + off, dst + off, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        CKP(cudaMemcpyAsync(optF + off, dF + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+        CKP(cudaMemcpyAsync(optX + off * n, dX + off * n, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
+        if (basis) CKP(cudaMemcpyAsync(basis + off * m, dB + off * m, sizeof(int64_t) * cnt * m, cudaMemcpyDeviceToHost, st));
+        if (stats) CKP(cudaMemcpyAsync(stats + off * 8, dS + off * 8, sizeof(int32_t) * cnt * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CKP(cudaEventRecord(ev[3 * chunks + 1], cs));
+    CKP(cudaStreamSynchronize(cs));
+    CKP(cudaStreamSynchronize(ks[0]));
+    CKP(cudaStreamSynchronize(ks[1]));
+    if (rc == GM_OK) {
+        t_timing.h2d_ms = ms(ev[3 * chunks], ev[3 * chunks + 1]);
+        double kms = 0;
+        for (int k = 0; k < chunks; ++k) kms += ms(ev[3 * k + 1], ev[3 * k + 2]);
+        t_timing.kernel_ms = kms;  // sum over chunk launches (they overlap the copies)
+        t_timing.d2h_ms = 0;
+    }
+    cudaFreeAsync(dc, cs); cudaFreeAsync(dA, cs); cudaFreeAsync(db, cs); cudaFreeAsync(dF, cs);
+    cudaFreeAsync(dX, cs); cudaFreeAsync(dst, cs);
+    if (dB) cudaFreeAsync(dB, cs);
+    if (dS) cudaFreeAsync(dS, cs);
+    cudaStreamSynchronize(cs);
+    cleanup();
+#undef CKP
+    return rc;
+}
+
 extern "C" {
 
 int gm_simplex_batch(int64_t count, const double* c, const double* A, const double* b, int64_t m, int64_t n,
@@ -367,6 +450,11 @@ int gm_simplex_batch(int64_t count, const double* c, const double* A, const doub
     std::memset(&P, 0, sizeof(P));
     P.c_stride = n; P.A_stride = m * n; P.b_stride = m;
     P.m0 = (int)m; P.n0 = (int)n; P.L = 0; P.tol = tol; P.count = (int)count; P.x_len = (int)n;
+    // pipeline when the input is big enough for PCIe time to matter and every chunk still fills the GPU
+    const double in_bytes = (double)count * (double)(m * n + m + n) * 8.0;
+    int chunks = (int)std::min<int64_t>(8, count / (4 * (int64_t)g.sms));
+    if (in_bytes < 32e6) chunks = 1;
+    if (chunks >= 2) return run_host_batch_pipelined(P, c, A, b, status, optF, optX, basis, stats, chunks);
     return run_host_call(P, c, A, n, b, nullptr, nullptr, nullptr, nullptr, status, optF, optX, basis, stats);
 }
 
