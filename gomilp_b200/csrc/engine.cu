@@ -410,13 +410,18 @@ static int run_host_batch_pipelined(gm::BatchParams P, const double* h_c, const 
         Q.stats = stats ? dS + off * 8 : nullptr;
         rc = launch_wave(Q, st, ev[3 * k + 1], ev[3 * k + 2], &t_timing);
         if (rc != GM_OK) break;
-        CKP(cudaMemcpyAsync(status + off, dst + off, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
-        CKP(cudaMemcpyAsync(optF + off, dF + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
-        CKP(cudaMemcpyAsync(optX + off * n, dX + off * n, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, st));
-        if (basis) CKP(cudaMemcpyAsync(basis + off * m, dB + off * m, sizeof(int64_t) * cnt * m, cudaMemcpyDeviceToHost, st));
-        if (stats) CKP(cudaMemcpyAsync(stats + off * 8, dS + off * 8, sizeof(int32_t) * cnt * 8, cudaMemcpyDeviceToHost, st));
     }
+    // results come back in one piece at the end: a device->host copy into pageable memory (a Go slice, a numpy
+    // array) blocks the calling thread, which inside the loop would serialise the chunks
     CKP(cudaEventRecord(ev[3 * chunks + 1], cs));
+    if (rc == GM_OK) {
+        for (int k = 0; k < chunks; ++k) CKP(cudaStreamWaitEvent(cs, ev[3 * k + 2], 0));
+        CKP(cudaMemcpyAsync(status, dst, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, cs));
+        CKP(cudaMemcpyAsync(optF, dF, sizeof(double) * count, cudaMemcpyDeviceToHost, cs));
+        CKP(cudaMemcpyAsync(optX, dX, sizeof(double) * count * n, cudaMemcpyDeviceToHost, cs));
+        if (basis) CKP(cudaMemcpyAsync(basis, dB, sizeof(int64_t) * count * m, cudaMemcpyDeviceToHost, cs));
+        if (stats) CKP(cudaMemcpyAsync(stats, dS, sizeof(int32_t) * count * 8, cudaMemcpyDeviceToHost, cs));
+    }
     CKP(cudaStreamSynchronize(cs));
     CKP(cudaStreamSynchronize(ks[0]));
     CKP(cudaStreamSynchronize(ks[1]));

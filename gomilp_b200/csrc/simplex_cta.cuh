@@ -657,18 +657,23 @@ struct SolverT {
             const double sel = reg_sel(k >> 2);
             double key = (q == kq && row >= k && row < m) ? fabs(sel) : -1.0;
             if (key != key) key = INFINITY;
-            // Idamax: first largest |.| in column k at or below the diagonal (dgetf2.go:43-45)
-            double km = key;
-            for (int d = 16; d >= 1; d >>= 1) km = fmax(km, gm_shfl_xor(km, d));
-            int idx = gm_warp_min_int(key == km ? row : INT_MAX);
-            if (lane == 0) { red[warp] = km; redi[warp] = idx; }
+            // Idamax: first largest |.| in column k at or below the diagonal (dgetf2.go:43-45). The bit
+            // pattern of a non-negative double is monotone, so two unsigned REDUX.MAX give the maximum
+            // and a REDUX.MIN over the rows that hold it gives the first one. key = -1 marks "not a candidate".
+            unsigned long long kb = key >= 0.0 ? gm_d2bits(key) : 0ull;
+            unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+            unsigned mh = gm_warp_max_u32(hi);
+            unsigned ml = gm_warp_max_u32(hi == mh ? lo : 0u);
+            int idx = gm_warp_min_int((key >= 0.0 && hi == mh && lo == ml) ? row : INT_MAX);
+            if (lane == 0) { redi[warp] = (int)mh; redi[32 + warp] = (int)ml; redi[64 + warp] = idx; }
             gm_sync();
-            key = red[lane & (nw - 1)];
-            idx = redi[lane & (nw - 1)];
-            km = key;
-            for (int d = 1; d < nw; d <<= 1) km = fmax(km, gm_shfl_xor(km, d));
-            idx = gm_warp_min_int(key == km ? idx : INT_MAX);
-            key = km;
+            hi = (unsigned)redi[lane & (nw - 1)];
+            lo = (unsigned)redi[32 + (lane & (nw - 1))];
+            idx = redi[64 + (lane & (nw - 1))];
+            mh = gm_warp_max_u32(hi);
+            ml = gm_warp_max_u32(hi == mh ? lo : 0u);
+            idx = gm_warp_min_int((hi == mh && lo == ml) ? idx : INT_MAX);
+            key = idx == INT_MAX ? -1.0 : gm_bits2d(((unsigned long long)mh << 32) | ml);
             if (!(key > 0.0) || key == INFINITY) { singular = 1; break; }
             const int p = idx;
             double f = gm_shfl_idx(sel, (lane & ~3) | kq);  // my row's entry in column k
@@ -1066,6 +1071,7 @@ struct SolverT {
             double bestv = INFINITY;
             int besti = INT_MAX;
             for (int k0 = 0; k0 < nn; k0 += 64) {
+                if (k0 + 8 * warp >= nn) break;  // warp-uniform: no column of this pass belongs to this warp
                 const int k = k0 + row;
                 const bool valid = k < nn;
                 const double* wc = W + (valid ? nonbasic[k] : 0) + q * ldw;
