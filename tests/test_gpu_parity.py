@@ -210,3 +210,24 @@ def test_knapsack_wave_root_and_first_levels():
     o = oracle.bnb_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, node_limit=1)
     assert g.log[0][3] == S.GM_OK and abs(g.log[0][4] - o.log["z"][0]) <= RTOL * abs(o.log["z"][0])
     assert g.status in (S.GM_MILP_OK, S.GM_MILP_DEADLINE_EXCEEDED)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_driver_single_rank():
+    """The multi-rank scheduler (gomilp_b200/sharded.py) over the C ABI with one rank == gm_milp_solve."""
+    from gomilp_b200.sharded import gpu_wave_solver, milp_solve_sharded
+    for case in PINS["milp"]:
+        r = milp_solve_sharded(case["c"], case["A"], case["b"], case["G"], case["h"], case["integrality"],
+                               solve_wave=gpu_wave_solver(), node_limit=200)
+        g = gm.milp_solve(case["c"], case["A"], case["b"], case["G"], case["h"], case["integrality"], node_limit=200)
+        assert r.status == g.status == MILP_STATUS[case["want_status"]] and r.nodes == g.nodes
+        assert [d[5] for d in r.decisions] == [l[5] for l in g.log]
+        if case["want_status"] == "OK":
+            assert _close(r.x, case["want_x"], 1e-12) and abs(r.z - case["want_z"]) <= 1e-12
+    rng = np.random.default_rng(8)
+    p = knapsack(rng, 24, 4)
+    r = milp_solve_sharded(p["c"], None, None, p["G"], p["h"], p["integrality"], solve_wave=gpu_wave_solver(),
+                           mode=S.GM_BNB_FIXED, heuristic=S.GM_BRANCH_MOST_INFEASIBLE, node_limit=500)
+    g = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED,
+                      heuristic=S.GM_BRANCH_MOST_INFEASIBLE, node_limit=500)
+    assert r.status == g.status and r.nodes == g.nodes and (r.z == g.z or (r.x is None and g.x is None))
