@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
 template <int T>
 __global__ void __launch_bounds__(T, 1) simplex_wave_hbm_all(gm::BatchParams P) {
     __shared__ int slot;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
     double* base = P.work + (size_t)blockIdx.x * P.work_stride;
     gm::cta_main<false>(P, base, base + w.big_doubles, &slot);
 }
@@ -106,7 +106,7 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     P.refactor_period = g.opt.refactor_period;
     const gm::WsLayout wr = gm::ws_layout(m, n, kSmemThreads, true);
     const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads);
-    const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads);
+    const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads, false, true);
     const size_t smem_reg = wr.big_bytes + wr.small_bytes;
     const size_t smem_all = w1.big_bytes + w1.small_bytes;
     const bool fits_reg = m <= 64 && smem_reg + 64 <= g.smem_optin;
@@ -137,6 +137,7 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         kern<<<grid, block, smem, stream>>>(P);
     } else {
         block = kHbmThreads;
+        P.hbm_layout = 1;
         const size_t per_cta = tier == 3 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8);
         grid = (int)std::min<long long>(P.count, (long long)g.sms);
         CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));

@@ -52,7 +52,8 @@ struct BatchParams {
     double tol;
     int count;
     int max_pivots;       // safety cap (the reference has none); <=0: 50*(m+n)+1000
-    int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100
+    int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100 (HBM tiers: max(100, 2m))
+    int hbm_layout;       // 1: W / Bi live in HBM (row strides padded to 32 B instead of to an odd count)
     // ---- outputs --------------------------------------------------------------------------------
     int* status;        // [count] gm_status
     double* optF;       // [count]
@@ -88,7 +89,7 @@ struct WsLayout {
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline WsLayout ws_layout(int m, int n, int T, bool reg = false) {
+inline WsLayout ws_layout(int m, int n, int T, bool reg = false, bool hbm = false) {
     WsLayout w;
     if (reg) {
         int ld = n + 1;
@@ -98,8 +99,8 @@ inline WsLayout ws_layout(int m, int n, int T, bool reg = false) {
         w.wrows = 64;
         w.vlen = 64;
     } else {
-        w.ldw = (n + 1) | 1;
-        w.ldb = m | 1;
+        w.ldw = hbm ? ((n + 1 + 3) & ~3) : ((n + 1) | 1);
+        w.ldb = hbm ? ((m + 3) & ~3) : (m | 1);
         w.wrows = m;
         w.vlen = m;
     }
@@ -279,51 +280,113 @@ struct SolverT {
     }
 
     // out[j] = (base ? base[j] : 0) + sgn * sum_i x[i] * M[i*ld + j]   (Dgemv Trans shape, vector.go:515-610)
+    // Lanes walk the contiguous dimension (coalesced / conflict free); the reduction dimension is cut in G
+    // contiguous row ranges, each walked 8 rows at a time with the 8 loads issued before the FMAs so that
+    // an HBM-resident M keeps 8 requests per thread in flight. A block of 8 rows whose x entries are all
+    // zero is skipped (Dgemv skips zero x too; duals and FTRAN columns are sparse on slack-heavy bases).
     GM_DEV void matvec_t(double* out, const double* base, double sgn, const double* M, int ld, int nr, int no,
                          const double* x) {
         const int t = gm_tid(), T = gm_nthreads();
-        if (no >= T) {
-            for (int j = t; j < no; j += T) {
-                double acc = 0;
-                for (int i = 0; i < nr; ++i) {
-                    const double xi = x[i];
-                    if (xi != 0) acc += xi * M[(size_t)i * ld + j];
-                }
-                out[j] = (base ? base[j] : 0.0) + sgn * acc;
-            }
-            gm_sync();
-            return;
-        }
-        const int S = pow2ceil(no);
+        int S = pow2ceil(no);
+        if (S > T) S = T;
         const int G = T / S;
         const int lane = t % S, g = t / S;
-        double acc = 0;
-        if (lane < no)
-            for (int i = g; i < nr; i += G) {
-                const double xi = x[i];
-                if (xi != 0) acc += xi * M[(size_t)i * ld + lane];
+        int chunk = (nr + G - 1) / G;
+        chunk = (chunk + 7) & ~7;
+        const int i0 = g * chunk, i1 = (i0 + chunk < nr) ? i0 + chunk : nr;
+        for (int j0 = 0; j0 < no; j0 += S) {
+            const int j = j0 + lane;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            if (j < no) {
+                const double* col = M + j;
+                int i = i0;
+                for (; i + 8 <= i1; i += 8) {
+                    double xv[8];
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { xv[u] = x[i + u]; any |= xv[u] != 0.0; }
+                    if (!any) continue;
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(i + u) * ld];
+                    a0 += xv[0] * v[0]; a1 += xv[1] * v[1]; a2 += xv[2] * v[2]; a3 += xv[3] * v[3];
+                    a0 += xv[4] * v[4]; a1 += xv[5] * v[5]; a2 += xv[6] * v[6]; a3 += xv[7] * v[7];
+                }
+                for (; i < i1; ++i) {
+                    const double xi = x[i];
+                    if (xi != 0.0) a0 += xi * col[(size_t)i * ld];
+                }
             }
-        red[t] = acc;
-        gm_sync();
-        if (t < no) {
-            double s = 0;
-            for (int g2 = 0; g2 < G; ++g2) s += red[g2 * S + t];
-            out[t] = (base ? base[t] : 0.0) + sgn * s;
+            const double acc = (a0 + a1) + (a2 + a3);
+            if (G == 1) {
+                if (j < no) out[j] = (base ? base[j] : 0.0) + sgn * acc;
+            } else {  // no <= S here: a single pass over j
+                red[t] = acc;
+                gm_sync();
+                if (t < no) {
+                    double sacc = 0;
+                    for (int g2 = 0; g2 < G; ++g2) sacc += red[g2 * S + t];
+                    out[t] = (base ? base[t] : 0.0) + sgn * sacc;
+                }
+            }
         }
         gm_sync();
     }
 
-    // out[i] = (base ? base[i] : 0) + sgn * sum_j M[i*ld + j] * x[j]   (one warp per row)
+    // out[i] = (base ? base[i] : 0) + sgn * sum_j M[i*ld + j] * x[j]   (one warp per row, 8 loads in flight per lane)
     GM_DEV void matvec_n(double* out, const double* base, double sgn, const double* M, int ld, int no, int nr,
                          const double* x) {
         const int t = gm_tid(), T = gm_nthreads();
         const int warp = t >> 5, lane = t & 31, nw = T >> 5;
         for (int i = warp; i < no; i += nw) {
-            double acc = 0;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             const double* row = M + (size_t)i * ld;
-            for (int j = lane; j < nr; j += 32) acc += row[j] * x[j];
+            int j = lane;
+            for (; j + 224 < nr; j += 256) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = row[j + 32 * u];
+                a0 += v[0] * x[j];       a1 += v[1] * x[j + 32];  a2 += v[2] * x[j + 64];  a3 += v[3] * x[j + 96];
+                a0 += v[4] * x[j + 128]; a1 += v[5] * x[j + 160]; a2 += v[6] * x[j + 192]; a3 += v[7] * x[j + 224];
+            }
+            for (; j < nr; j += 32) a0 += row[j] * x[j];
+            double acc = (a0 + a1) + (a2 + a3);
             for (int d = 16; d >= 1; d >>= 1) acc += gm_shfl_xor(acc, d);
             if (lane == 0) out[i] = (base ? base[i] : 0.0) + sgn * acc;
+        }
+        gm_sync();
+    }
+
+    // M[i][j] <- (i == l) ? prw[j] : M[i][j] - f[i] * prw[j]   for i, j < mm, and with zero_col >= 0 the old
+    // M[i][zero_col] is taken as 0 (the in-place Gauss-Jordan trick). Rows are walked 8 at a time with the
+    // 8 loads issued before the stores; a block of 8 rows with all f == 0 (and not holding row l) is skipped.
+    GM_DEV void rank1_update(double* M, int ld, int mm, int l, const double* f, const double* prw, int zero_col) {
+        const int t = gm_tid(), T = gm_nthreads();
+        for (int i0 = 0; i0 < mm; i0 += 8) {
+            const int cnt = mm - i0 < 8 ? mm - i0 : 8;
+            double fv[8];
+            bool any = (l >= i0 && l < i0 + cnt);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { fv[u] = u < cnt ? f[i0 + u] : 0.0; any |= fv[u] != 0.0; }
+            if (!any) continue;
+            for (int j = t; j < mm; j += T) {
+                const double pj = prw[j];
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (u < cnt) v[u] = M[(size_t)(i0 + u) * ld + j];
+                if (j == zero_col) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u < cnt) {
+                        if (i0 + u == l) M[(size_t)(i0 + u) * ld + j] = pj;
+                        else if (fv[u] != 0.0) M[(size_t)(i0 + u) * ld + j] = v[u] - fv[u] * pj;
+                    }
+                }
+            }
         }
         gm_sync();
     }
@@ -532,15 +595,7 @@ struct SolverT {
             const double ap = alv[l];
             for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] / ap;
             gm_sync();
-            for_each_2d(m, m, [&](int i, int j) {
-                if (i == l) {
-                    Bi[(size_t)i * ldb + j] = prow[j];
-                } else {
-                    const double f = alv[i];
-                    if (f != 0.0) Bi[(size_t)i * ldb + j] -= f * prow[j];
-                }
-            });
-            gm_sync();
+            rank1_update(Bi, ldb, m, l, alv, prow, -1);
         }
     }
 
@@ -584,18 +639,7 @@ struct SolverT {
             for (int i = t; i < m; i += T) t1[i] = Bi[(size_t)i * ldb + k];
             for (int j = t; j < m; j += T) prow[j] = (j == k ? 1.0 : Bi[(size_t)k * ldb + j]) / pv;
             gm_sync();
-            for_each_2d(m, m, [&](int i, int j) {
-                if (i == k) {
-                    Bi[(size_t)i * ldb + j] = prow[j];
-                } else {
-                    const double f = t1[i];
-                    if (f != 0.0) {
-                        const double base = (j == k) ? 0.0 : Bi[(size_t)i * ldb + j];
-                        Bi[(size_t)i * ldb + j] = base - f * prow[j];
-                    }
-                }
-            });
-            gm_sync();
+            rank1_update(Bi, ldb, m, k, t1, prow, k);
         }
         if (singular) {
             *cond1 = INFINITY;
@@ -1407,7 +1451,7 @@ struct SolverT {
     GM_DEV void bind_workspace(const BatchParams& P, double* big, double* small) {
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
-        const WsLayout w = ws_layout(m, n, gm_nthreads(), REG);
+        const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0);
         ldw = w.ldw; ldb = w.ldb; wrows = w.wrows; vlen = w.vlen;
         W = big + w.W; Bi = big + w.Bi;
         xb = small + w.xb; cb = small + w.cb; y = small + w.y; al = small + w.al;
@@ -1417,7 +1461,7 @@ struct SolverT {
         basic = iw + w.basic; nonbasic = iw + w.nonbasic; inb = iw + w.inb; redi = iw + w.redi; ipiv = iw + w.ipiv;
         cperm = iw + w.cperm;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
-        refactor_period = P.refactor_period > 0 ? P.refactor_period : 100;
+        refactor_period = P.refactor_period > 0 ? P.refactor_period : (P.hbm_layout && 2 * m > 100 ? 2 * m : 100);
     }
     GM_DEV void bind_lp(const BatchParams& P, int lp) {
         c0 = P.c + (size_t)lp * P.c_stride;
