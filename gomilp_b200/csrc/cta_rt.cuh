@@ -32,4 +32,35 @@ GM_DEV int gm_shfl_idx(int v, int src) { return __shfl_sync(0xffffffffu, v, src)
 GM_DEV int gm_any(int pred) { return __any_sync(0xffffffffu, pred); }
 GM_DEV int gm_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 GM_DEV double gm_ldg(const double* p) { return __ldg(p); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on a shared-memory mbarrier -------------------
+GM_DEV unsigned gm_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+GM_DEV void gm_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(count) : "memory");
+}
+GM_DEV void gm_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+GM_DEV void gm_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst (shared, 16 B aligned) <- src (global, 16 B aligned), bytes a multiple of 16
+GM_DEV void gm_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     gm_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(gm_smem_u32(bar))
+                 : "memory");
+}
+// Waits for the phase with the given parity; bounded so that a programming error cannot hang the GPU.
+GM_DEV bool gm_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = gm_smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
 #endif

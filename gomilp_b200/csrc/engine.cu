@@ -40,9 +40,13 @@ __global__ void __launch_bounds__(T, MINB) simplex_wave_smem(gm::BatchParams P) 
 // big part (W, Bi) in HBM, small part in shared memory
 template <int T>
 __global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
     __shared__ int slot;
-    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, &slot);
+    __shared__ unsigned long long bars[8];
+    // [TMA staging ring | vectors, lists]
+    const size_t ring_doubles = (size_t)P.ring_stages * (P.ring_stage_bytes / 8);
+    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem + ring_doubles, &slot,
+                        P.ring_stages > 0 ? smem : nullptr, bars);
 }
 
 // everything in HBM (very large m + n)
@@ -144,7 +148,14 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         P.work = work;
         P.work_stride = (long long)per_cta;
         if (tier == 3) {
-            smem = w2.small_bytes;
+            // TMA staging ring: up to 3 stages of 32 KB if they fit beside the vectors
+            const size_t stage = 32768;
+            long long room = (long long)g.smem_optin - (long long)w2.small_bytes - 256;
+            int ns = (int)std::min<long long>(3, room / (long long)stage);
+            if (ns < 2 || g.opt.reserved == 1) ns = 0;  // options.reserved = 1 disables the ring (A/B measurements)
+            P.ring_stages = ns;
+            P.ring_stage_bytes = ns ? (int)stage : 0;
+            smem = w2.small_bytes + (size_t)ns * stage;
             auto kern = simplex_wave_hbm<kHbmThreads>;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (ev0) CK(cudaEventRecord(ev0, stream));

@@ -53,6 +53,7 @@ struct BatchParams {
     int count;
     int max_pivots;       // safety cap (the reference has none); <=0: 50*(m+n)+1000
     int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100 (HBM tiers: max(100, 2m))
+    int ring_stages, ring_stage_bytes;  // HBM tier: TMA staging ring in shared memory (0: none)
     int hbm_layout;       // 1: W / Bi live in HBM (row strides padded to 32 B instead of to an odd count)
     // ---- outputs --------------------------------------------------------------------------------
     int* status;        // [count] gm_status
@@ -99,7 +100,7 @@ inline WsLayout ws_layout(int m, int n, int T, bool reg = false, bool hbm = fals
         w.wrows = 64;
         w.vlen = 64;
     } else {
-        w.ldw = hbm ? ((n + 1 + 3) & ~3) : ((n + 1) | 1);
+        w.ldw = hbm ? ((n + 2 + 3) & ~3) : ((n + 1) | 1);
         w.ldb = hbm ? ((m + 3) & ~3) : (m | 1);
         w.wrows = m;
         w.vlen = m;
@@ -159,6 +160,11 @@ struct SolverT {
     int ncols, nn;  // current width of W and number of non-basic columns
     int wrows, vlen;  // rows of W incl. zero padding; length of the m-vectors incl. zero padding
     double anorm_w;  // norm of the basis at its last inversion, scale of the polish residual test
+    // HBM tier: ring of shared-memory stages fed by TMA bulk copies (nullptr: plain loads)
+    double* ring;
+    unsigned long long* ring_bar;
+    int ring_stage_doubles, ring_ns, ring_uses;
+    int* sel;  // row list of the current stream (aliases inb: the flags are dead inside the main loop)
     bool w_loaded;   // REG tier: W holds [A | art] in ORIGINAL column order for the current LP
     // counters (uniform across the CTA)
     int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
@@ -1016,6 +1022,9 @@ struct SolverT {
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
         if constexpr (REG) return main_loop_reg(tol, phase, fresh);
+        if (ring != nullptr && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
+            ((m + 1) & ~1) <= ring_stage_doubles)
+            return main_loop_stream(tol, phase, fresh);
         const int t = gm_tid(), T = gm_nthreads();
         int since = 0;
         for (;;) {
@@ -1243,6 +1252,242 @@ struct SolverT {
         }
     }
 
+    // =================================================================================================
+    // HBM tier: TMA-staged streaming of W / Bi rows (cp.async.bulk -> mbarrier -> all threads consume)
+    // =================================================================================================
+    // Streams rows sel[0..nsel) of a row-major HBM matrix, columns [c0, c0 + wcols) (c0 even, wcols even: 16 B
+    // alignment), through `ring_ns` stages. One elected thread issues one bulk copy per row; every thread
+    // waits on the stage's mbarrier, calls tile(stage, first, count) and releases the stage at a barrier.
+    // Returns false if a copy never completes (reported as GM_ERR_CUDA by the caller, never a hang).
+    template <class F>
+    GM_DEV bool stream_rows(const double* M, int ld, int c0, int wcols, int nsel, F tile) {
+        const int t = gm_tid();
+        int R = ring_stage_doubles / wcols;
+        if (R > 64) R = 64;
+        const int ntiles = (nsel + R - 1) / R;
+        const unsigned row_bytes = (unsigned)wcols * 8u;
+        const int use0 = ring_uses;  // barrier k%ns has completed (use0 + k)/ns phases before this stream... per-stage counters below
+        auto issue = [&](int k) {
+            if (t == 0) {
+                const int first = k * R;
+                const int cnt = nsel - first < R ? nsel - first : R;
+                const int sidx = (use0 + k) % ring_ns;
+                double* st = ring + (size_t)sidx * ring_stage_doubles;
+                gm_mbar_expect_tx(ring_bar + sidx, row_bytes * (unsigned)cnt);
+                for (int u = 0; u < cnt; ++u)
+                    gm_bulk_g2s(st + (size_t)u * wcols, M + (size_t)sel[first + u] * ld + c0, row_bytes, ring_bar + sidx);
+            }
+        };
+        const int pre = ntiles < ring_ns ? ntiles : ring_ns;
+        for (int k = 0; k < pre; ++k) issue(k);
+        bool ok = true;
+        for (int k = 0; k < ntiles; ++k) {
+            const int g = use0 + k;
+            const int sidx = g % ring_ns;
+            if (!gm_mbar_wait(ring_bar + sidx, (unsigned)((g / ring_ns) & 1))) ok = false;
+            const int first = k * R;
+            const int cnt = nsel - first < R ? nsel - first : R;
+            tile(ring + (size_t)sidx * ring_stage_doubles, first, cnt);
+            gm_sync();  // stage consumed by everybody: it may be refilled
+            if (k + ring_ns < ntiles) issue(k + ring_ns);
+        }
+        ring_uses = use0 + ntiles;
+        return ok;
+    }
+
+    // Builds sel[] = ascending list of i in [0, count) with pred(i); returns its length (ballot compaction).
+    template <class F>
+    GM_DEV int select_rows(int count, F pred) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        int base = 0;
+        for (int i0 = 0; i0 < count; i0 += T) {
+            const int i = i0 + t;
+            const int flag = (i < count) && pred(i);
+            const unsigned bal = gm_ballot(flag);
+            if (lane == 0) redi[warp] = gm_popc(bal);
+            gm_sync();
+            int off = base, tot = 0;
+            for (int w = 0; w < nw; ++w) {
+                const int c = redi[w];
+                if (w < warp) off += c;
+                tot += c;
+            }
+            if (flag) sel[off + gm_popc(bal & ((1u << lane) - 1u))] = i;
+            base += tot;
+            gm_sync();
+        }
+        return base;
+    }
+
+    // The simplex main loop of the HBM tier (same decisions as main_loop, simplex.go:233-293). Per pivot:
+    //   pricing   rows of W with y_i != 0 stream through the ring; thread j accumulates column j      (m(n-m) words)
+    //   FTRAN     a sparse entering column gathers columns of Bi, a dense one streams all of Bi      (m^2 words)
+    //   update    only rows with alpha_i != 0 stream in, are updated and stored back coalesced       (2 m^2 words)
+    GM_DEV int main_loop_stream(double tol, int phase, bool fresh) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        constexpr int JMAX = 8;
+        int since = 0;
+        for (;;) {
+            if (piv1 + piv2 >= max_pivots) return GM_ERR_ITERATION_LIMIT;
+            // ---- pricing: r = cn - an^T y over the non-basic columns [m, m + nn) of W
+            {
+                const int c0 = m & ~1;              // aligned start: one basic column may ride along
+                const int off = m - c0;
+                const int wcols = (nn + off + 1) & ~1;
+                double acc[JMAX];
+#pragma unroll
+                for (int jj = 0; jj < JMAX; ++jj) acc[jj] = 0.0;
+                const int nsel = select_rows(m, [&](int i) { return y[i] != 0.0; });
+                const bool ok = stream_rows(W, ldw, c0, wcols, nsel, [&](const double* st, int first, int cnt) {
+                    for (int u = 0; u < cnt; ++u) {
+                        const double yi = y[sel[first + u]];
+                        const double* rowp = st + (size_t)u * wcols;
+#pragma unroll
+                        for (int jj = 0; jj < JMAX; ++jj) {
+                            const int j = t + jj * T;
+                            if (j < wcols) acc[jj] += yi * rowp[j];
+                        }
+                    }
+                });
+                if (!ok) return GM_ERR_CUDA;
+#pragma unroll
+                for (int jj = 0; jj < JMAX; ++jj) {
+                    const int k = t + jj * T - off;
+                    if (k >= 0 && k < nn) r[k] = cn[k] - acc[jj];
+                }
+                gm_sync();
+            }
+            MinLoc rl = block_argmin(nn, [&](int k) { return r[k]; });
+            if (rl.v >= -tol || rl.v != rl.v) {
+                if (!fresh) {
+                    const int rc = polish();
+                    if (rc != GM_OK) return rc;
+                    fresh = true;
+                    continue;
+                }
+                return GM_OK;
+            }
+            int e = rl.i;
+            double re = rl.v;
+            for (int k = t; k < nn; k += T)
+                if (fabs(r[k]) < GM_R_ROUND_TOL) r[k] = 0.0;  // :252-256
+            gm_sync();
+            int rc = compute_move_stream(e);
+            if (rc != GM_OK) return rc;
+            MinLoc ml = block_argmin(m, [&](int q) { return mv[q]; });
+            int l = ml.i;
+            if (ml.v <= 0.0) {  // :268-277
+                nbland++;
+                rc = replace_bland(l, e);
+                if (rc != GM_OK) return rc;
+                re = r[e];
+            }
+            // ---- basis change: only the rows with alpha_i != 0 move
+            {
+                const double ap = al[l];
+                const double theta = xb[l] / ap;
+                const double inv = 1.0 / ap;
+                for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] * inv;
+                gm_sync();
+                const int mA = (m + 1) & ~1;
+                const int nsel = select_rows(m, [&](int i) { return i == l || al[i] != 0.0; });
+                const bool ok = stream_rows(Bi, ldb, 0, mA, nsel, [&](const double* st, int first, int cnt) {
+                    for (int u = 0; u < cnt; ++u) {
+                        const int i = sel[first + u];
+                        const double f = al[i];
+                        const double* rowp = st + (size_t)u * mA;
+                        double* dst = Bi + (size_t)i * ldb;
+                        if (i == l) {
+                            for (int j = t; j < m; j += T) dst[j] = prow[j];
+                        } else {
+                            for (int j = t; j < m; j += T) dst[j] = rowp[j] - f * prow[j];
+                        }
+                    }
+                });
+                if (!ok) return GM_ERR_CUDA;
+                for (int i = t; i < m; i += T) {
+                    xb[i] = (i == l) ? theta : xb[i] - al[i] * theta;
+                    y[i] += re * prow[i];
+                    const double a = W[(size_t)i * ldw + l];
+                    W[(size_t)i * ldw + l] = W[(size_t)i * ldw + m + e];
+                    W[(size_t)i * ldw + m + e] = a;
+                }
+                if (t == 0) {
+                    const int v = basic[l];
+                    basic[l] = nonbasic[e];
+                    nonbasic[e] = v;
+                    const double cc = cb[l];
+                    cb[l] = cn[e];
+                    cn[e] = cc;
+                }
+                gm_sync();
+            }
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            if (++since >= refactor_period) {
+                rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+            }
+            (void)lane; (void)warp; (void)nw;
+        }
+    }
+
+    // computeMove for the HBM tier: al = Bi a_e with a_e = column m+e of W.
+    GM_DEV int compute_move_stream(int e) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + m + e];
+        gm_sync();
+        const int nz = select_rows(m, [&](int i) { return t1[i] != 0.0; });
+        if (nz * 4 <= m) {
+            // sparse column (a slack has one entry): al = sum_j a_j Bi[:, j], one strided gather per non-zero
+            for (int i = t; i < m; i += T) {
+                double acc = 0;
+                const double* rowp = Bi + (size_t)i * ldb;
+                for (int u = 0; u < nz; ++u) {
+                    const int j = sel[u];
+                    acc += rowp[j] * t1[j];
+                }
+                al[i] = acc;
+            }
+            gm_sync();
+        } else {
+            const int mA = (m + 1) & ~1;
+            for (int i = t; i < m; i += T) sel[i] = i;
+            gm_sync();
+            const bool ok = stream_rows(Bi, ldb, 0, mA, m, [&](const double* st, int first, int cnt) {
+                for (int u = warp; u < cnt; u += nw) {
+                    const double* rowp = st + (size_t)u * mA;
+                    double a0 = 0, a1 = 0;
+                    int j = lane;
+                    for (; j + 32 < m; j += 64) {
+                        a0 += rowp[j] * t1[j];
+                        a1 += rowp[j + 32] * t1[j + 32];
+                    }
+                    if (j < m) a0 += rowp[j] * t1[j];
+                    double acc = a0 + a1;
+                    for (int d = 16; d >= 1; d >>= 1) acc += gm_shfl_xor(acc, d);
+                    if (lane == 0) al[first + u] = acc;
+                }
+            });
+            if (!ok) return GM_ERR_CUDA;
+        }
+        for (int i = t; i < m; i += T) {
+            double d = -al[i];
+            if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+            mv[i] = d < 0.0 ? xb[i] / fabs(d) : INFINITY;
+            t2[i] = d;
+        }
+        gm_sync();
+        const int anyneg = block_min_int(m, [&](int i) { return t2[i] < 0.0 ? i : INT_MAX; });
+        if (anyneg == INT_MAX) return GM_ERR_UNBOUNDED;
+        return GM_OK;
+    }
+
     // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
     GM_DEV int find_initial_basic(bool& fresh) {
         const int t = gm_tid(), T = gm_nthreads();
@@ -1448,7 +1693,10 @@ struct SolverT {
     }
 
     // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
-    GM_DEV void bind_workspace(const BatchParams& P, double* big, double* small) {
+    GM_DEV void bind_workspace(const BatchParams& P, double* big, double* small, double* ring_base = nullptr,
+                               unsigned long long* bars = nullptr) {
+        ring = ring_base; ring_bar = bars; ring_ns = P.ring_stages; ring_stage_doubles = P.ring_stage_bytes / 8;
+        ring_uses = 0;
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
         const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0);
@@ -1460,6 +1708,7 @@ struct SolverT {
         int* iw = reinterpret_cast<int*>(small + w.small_doubles);
         basic = iw + w.basic; nonbasic = iw + w.nonbasic; inb = iw + w.inb; redi = iw + w.redi; ipiv = iw + w.ipiv;
         cperm = iw + w.cperm;
+        sel = inb;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
         refactor_period = P.refactor_period > 0 ? P.refactor_period : (P.hbm_layout && 2 * m > 100 ? 2 * m : 100);
     }
@@ -1476,9 +1725,17 @@ struct SolverT {
 
 // Persistent CTA: pulls LP indices from a global counter until the batch is exhausted.
 template <bool REG>
-GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */) {
+GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */,
+                     double* ring = nullptr, unsigned long long* bars = nullptr) {
     SolverT<REG> s;
-    s.bind_workspace(P, big, small);
+    s.bind_workspace(P, big, small, ring, bars);
+    if (ring != nullptr) {
+        if (gm_tid() == 0) {
+            for (int k = 0; k < P.ring_stages; ++k) gm_mbar_init(bars + k, 1);
+            gm_mbar_fence_init();
+        }
+        gm_sync();
+    }
     for (;;) {
         if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
         gm_sync();

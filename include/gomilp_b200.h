@@ -51,7 +51,7 @@ typedef struct gm_options {
     int32_t max_pivots;      /* safety cap per LP; the reference has none. default 50*(m+n)+1000 */
     int32_t refactor_period; /* pivots between rebuilds of the basis inverse. default 100 */
     int32_t force_tier;      /* 0 auto, else the gm_timing.tier to force (GM_ERR_TOO_LARGE if it does not fit) */
-    int32_t reserved;
+    int32_t reserved;        /* 1: tier 3 without the TMA staging ring (plain loads), for A/B measurements */
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
 

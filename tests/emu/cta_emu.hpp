@@ -258,3 +258,32 @@ inline int gm_atomic_add(int* p, int v) {
     return o;
 }
 inline double gm_ldg(const double* p) { return *p; }
+
+// ---- TMA bulk copy + mbarrier stand-ins: the copy happens at issue time, the barrier counts bytes ----------
+// An emulated mbarrier word: low 32 bits = bytes still expected in the current phase (two's complement while
+// copies outrun expect_tx), bit 63 = current phase parity.
+inline void gm_mbar_init(unsigned long long* bar, int) { *bar = 0; }
+inline void gm_mbar_fence_init() {}
+inline void emu_mbar_add(unsigned long long* bar, long long delta, bool is_expect) {
+    long long pending = (long long)(int)(unsigned)(*bar & 0xffffffffull);
+    unsigned long long phase = *bar >> 63;
+    unsigned long long armed = (*bar >> 62) & 1ull;
+    pending += delta;
+    if (is_expect) armed = 1;
+    if (armed && pending == 0) { phase ^= 1ull; armed = 0; }
+    *bar = (phase << 63) | (armed << 62) | (unsigned long long)(unsigned)(int)pending;
+}
+inline void gm_mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu_mbar_add(bar, (long long)bytes, true); }
+inline void gm_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15))
+        throw std::runtime_error("cta_emu: misaligned bulk copy");
+    std::memcpy(dst, src, bytes);
+    emu_mbar_add(bar, -(long long)bytes, false);
+}
+inline bool gm_mbar_wait(unsigned long long* bar, unsigned parity) {
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        if ((unsigned)(*bar >> 63) != parity) return true;  // the phase with this parity has completed
+        emu::yield_as(emu::RUN);
+    }
+    return false;
+}

@@ -14,7 +14,8 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
                       long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
                       const double* bsign, const double* brhs, const long long* initial_basic, double tol,
                       int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
-                      int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg) {
+                      int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg, int ring_stages,
+                      int ring_stage_bytes) {
     gm::BatchParams P;
     std::memset(&P, 0, sizeof(P));
     P.c = c; P.A = A; P.b = b;
@@ -28,12 +29,20 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
     int queue = 0;
     P.queue = &queue;
     if (reg && (T != 256 || m0 + L > 64)) return -2;
-    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T, reg != 0);
-    std::vector<double> big(w.big_doubles + 8, 0.0), small(w.small_bytes / 8 + 8, 0.0);
+    const bool hbm = ring_stages > 0;
+    P.hbm_layout = hbm ? 1 : 0;
+    P.ring_stages = ring_stages;
+    P.ring_stage_bytes = ring_stage_bytes;
+    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T, reg != 0, hbm);
+    std::vector<double> ringbuf((size_t)ring_stages * ring_stage_bytes / 8 + 32, 0.0);
+    double* ring = hbm ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ringbuf.data()) + 127) & ~uintptr_t(127)) : nullptr;
+    unsigned long long bars[8] = {0};
+    std::vector<double> bigbuf(w.big_doubles + 40, 0.0), small(w.small_bytes / 8 + 8, 0.0);
+    double* big = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(bigbuf.data()) + 127) & ~uintptr_t(127));
     int slot = 0;
     try {
-        if (reg) emu::run_cta(T, [&]() { gm::cta_main<true>(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
-        else emu::run_cta(T, [&]() { gm::cta_main<false>(P, big.data(), small.data(), &slot); }, shuffle_order != 0);
+        if (reg) emu::run_cta(T, [&]() { gm::cta_main<true>(P, big, small.data(), &slot); }, shuffle_order != 0);
+        else emu::run_cta(T, [&]() { gm::cta_main<false>(P, big, small.data(), &slot, ring, bars); }, shuffle_order != 0);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return -1;
@@ -81,7 +90,7 @@ int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar,
     int rc = emu_simplex_batch((int)nodes, r.c.data(), r.A.data(), r.b.data(), 0, 0, 0, r.n0, r.m0, r.n0, (int)L, bvar,
                                bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0,
                                reinterpret_cast<long long*>(basis), stats, g_T, 0,
-                               (g_reg && r.m0 + (int)L <= 64) ? 1 : 0);
+                               (g_reg && r.m0 + (int)L <= 64) ? 1 : 0, 0, 0);
     return rc == 0 ? GM_OK : GM_ERR_CUDA;
 }
 }  // extern "C"

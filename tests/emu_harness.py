@@ -45,7 +45,7 @@ def _p(a):
 
 
 def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_basic=None, T=64,
-                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False, reg=False):
+                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False, reg=False, ring_stages=0, ring_stage_bytes=4096):
     """Batch of LPs through the emulated kernel.
 
     Plain batch: A [count,m,n], c [count,n], b [count,m]. Wave mode (shared_root=True): one root
@@ -80,7 +80,7 @@ def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_ba
                                  _p(bsign), _p(brhs), _p(ib), C.c_double(tol), C.c_int(max_pivots),
                                  C.c_int(refactor_period), _p(status), _p(optF), _p(x), C.c_longlong(x_len),
                                  C.c_int(x_len), _p(basis), _p(stats), C.c_int(256 if reg else T), C.c_int(int(shuffle_order)),
-                                 C.c_int(int(reg)))
+                                 C.c_int(int(reg)), C.c_int(ring_stages), C.c_int(ring_stage_bytes if ring_stages else 0))
     if rc != 0:
         raise RuntimeError("CTA emulator: barrier divergence" if rc == -1 else "CTA emulator: bad tier request")
     return {"status": status, "optF": optF, "x": x, "basis": basis, "stats": stats}

@@ -108,6 +108,12 @@ def test_every_tier_matches_oracle():
     o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads())
     assert (g["status"] == o["status"]).all()
     assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
+    gm.set_options(no_tma_ring=True)   # tier 3 with plain loads instead of the TMA staging ring
+    try:
+        g2 = gm.simplex_batch(c, A, b)
+    finally:
+        gm.set_options()
+    assert (g2["status"] == o["status"]).all() and _close(g2["x"], o["x"])
     c, A, b = feasible_bounded_lp(rng, 16, 40, 32)
     c2, A2, b2 = raw_lp(rng, 9, 17, 64, 0.2)
     o = oracle.simplex_batch(c, A, b)
