@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(T, MINB) simplex_wave_reg(gm::BatchParams P) {
     extern __shared__ double smem[];
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, true);
-    gm::cta_main<true>(P, smem, smem + w.big_doubles, &slot);
+    gm::cta_main<true>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
 }
 
 // tier 2: W, Bi and vectors in shared memory
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(T, MINB) simplex_wave_smem(gm::BatchParams P) 
     extern __shared__ double smem[];
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
-    gm::cta_main<false>(P, smem, smem + w.big_doubles, &slot);
+    gm::cta_main<false>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
 }
 
 // big part (W, Bi) in HBM, small part in shared memory
@@ -45,8 +45,19 @@ __global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
     __shared__ unsigned long long bars[8];
     // [TMA staging ring | vectors, lists]
     const size_t ring_doubles = (size_t)P.ring_stages * (P.ring_stage_bytes / 8);
-    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem + ring_doubles, &slot,
-                        P.ring_stages > 0 ? smem : nullptr, bars);
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
+    double* base = P.work + (size_t)blockIdx.x * P.work_stride;
+    gm::cta_main<false>(P, base + w.W, base + w.Bi, smem + ring_doubles, &slot, P.ring_stages > 0 ? smem : nullptr, bars);
+}
+
+// tier 3: basis inverse + vectors in shared memory, W in HBM
+template <int T>
+__global__ void __launch_bounds__(T, 1) simplex_wave_bismem(gm::BatchParams P) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
+    const size_t bi_doubles = w.big_doubles - w.Bi;
+    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, smem + bi_doubles, &slot);
 }
 
 // everything in HBM (very large m + n)
@@ -55,7 +66,7 @@ __global__ void __launch_bounds__(T, 1) simplex_wave_hbm_all(gm::BatchParams P) 
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
     double* base = P.work + (size_t)blockIdx.x * P.work_stride;
-    gm::cta_main<false>(P, base, base + w.big_doubles, &slot);
+    gm::cta_main<false>(P, base + w.W, base + w.Bi, base + w.big_doubles, &slot);
 }
 
 struct Root {
@@ -116,9 +127,12 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     const bool fits_reg = m <= 64 && smem_reg + 64 <= g.smem_optin;
     const bool fits_smem = smem_all + 64 <= g.smem_optin;
     const bool fits_small = w2.small_bytes + 64 <= g.smem_optin;
+    const size_t bi_bytes = (w2.big_doubles - w2.Bi) * sizeof(double);
+    const bool fits_bismem = bi_bytes + w2.small_bytes + 64 <= g.smem_optin;
     int tier = g.opt.force_tier;
-    if (tier == 0) tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_small ? 3 : 4));
-    if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_small) || tier < 1 || tier > 4)
+    if (tier == 0) tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_bismem ? 3 : (fits_small ? 4 : 5)));
+    if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_bismem) ||
+        (tier == 4 && !fits_small) || tier < 1 || tier > 5)
         return GM_ERR_TOO_LARGE;
 
     int* queue = nullptr;
@@ -142,12 +156,19 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     } else {
         block = kHbmThreads;
         P.hbm_layout = 1;
-        const size_t per_cta = tier == 3 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8);
+        // per-CTA HBM slice: W only (tier 3), W + Bi (tier 4), everything (tier 5)
+        const size_t per_cta = tier == 3 ? w2.Bi : (tier == 4 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8));
         grid = (int)std::min<long long>(P.count, (long long)g.sms);
         CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));
         P.work = work;
         P.work_stride = (long long)per_cta;
         if (tier == 3) {
+            smem = bi_bytes + w2.small_bytes;
+            auto kern = simplex_wave_bismem<kHbmThreads>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (ev0) CK(cudaEventRecord(ev0, stream));
+            kern<<<grid, block, smem, stream>>>(P);
+        } else if (tier == 4) {
             // TMA staging ring: up to 3 stages of 32 KB if they fit beside the vectors
             const size_t stage = 32768;
             long long room = (long long)g.smem_optin - (long long)w2.small_bytes - 256;

@@ -1022,7 +1022,7 @@ struct SolverT {
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
         if constexpr (REG) return main_loop_reg(tol, phase, fresh);
-        if (ring != nullptr && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
+        if (ring != nullptr && m >= 384 && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
             ((m + 1) & ~1) <= ring_stage_doubles)
             return main_loop_stream(tol, phase, fresh);
         const int t = gm_tid(), T = gm_nthreads();
@@ -1693,15 +1693,15 @@ struct SolverT {
     }
 
     // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
-    GM_DEV void bind_workspace(const BatchParams& P, double* big, double* small, double* ring_base = nullptr,
-                               unsigned long long* bars = nullptr) {
+    GM_DEV void bind_workspace(const BatchParams& P, double* wbase, double* bibase, double* small,
+                               double* ring_base = nullptr, unsigned long long* bars = nullptr) {
         ring = ring_base; ring_bar = bars; ring_ns = P.ring_stages; ring_stage_doubles = P.ring_stage_bytes / 8;
         ring_uses = 0;
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
         const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0);
         ldw = w.ldw; ldb = w.ldb; wrows = w.wrows; vlen = w.vlen;
-        W = big + w.W; Bi = big + w.Bi;
+        W = wbase; Bi = bibase;
         xb = small + w.xb; cb = small + w.cb; y = small + w.y; al = small + w.al;
         mv = small + w.mv; bv = small + w.bv; prow = small + w.prow; art = small + w.art; t1 = small + w.t1;
         t2 = small + w.t2; cn = small + w.cn; r = small + w.r; red = small + w.red;
@@ -1725,10 +1725,10 @@ struct SolverT {
 
 // Persistent CTA: pulls LP indices from a global counter until the batch is exhausted.
 template <bool REG>
-GM_DEV void cta_main(const BatchParams& P, double* big, double* small, int* slot /* CTA-shared int */,
-                     double* ring = nullptr, unsigned long long* bars = nullptr) {
+GM_DEV void cta_main(const BatchParams& P, double* wbase, double* bibase, double* small,
+                     int* slot /* CTA-shared int */, double* ring = nullptr, unsigned long long* bars = nullptr) {
     SolverT<REG> s;
-    s.bind_workspace(P, big, small, ring, bars);
+    s.bind_workspace(P, wbase, bibase, small, ring, bars);
     if (ring != nullptr) {
         if (gm_tid() == 0) {
             for (int k = 0; k < P.ring_stages; ++k) gm_mbar_init(bars + k, 1);

@@ -41,7 +41,8 @@ typedef struct gm_timing {
     int64_t launches;   /* kernel launches */
     int64_t smem_bytes; /* dynamic shared memory per CTA (0: HBM-resident tier) */
     int32_t tier;       /* 1 = basis inverse in registers + W in shared memory (m <= 64), 2 = all in shared memory,
-                           3 = W / inverse in HBM + vectors in shared memory, 4 = all in HBM */
+                           3 = inverse + vectors in shared memory, W in HBM, 4 = W and inverse in HBM behind a TMA
+                           staging ring, vectors in shared memory, 5 = all in HBM */
     int32_t grid, block;
 } gm_timing;
 int gm_last_timing(gm_timing* out);

@@ -41,8 +41,8 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
     double* big = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(bigbuf.data()) + 127) & ~uintptr_t(127));
     int slot = 0;
     try {
-        if (reg) emu::run_cta(T, [&]() { gm::cta_main<true>(P, big, small.data(), &slot); }, shuffle_order != 0);
-        else emu::run_cta(T, [&]() { gm::cta_main<false>(P, big, small.data(), &slot, ring, bars); }, shuffle_order != 0);
+        if (reg) emu::run_cta(T, [&]() { gm::cta_main<true>(P, big + w.W, big + w.Bi, small.data(), &slot); }, shuffle_order != 0);
+        else emu::run_cta(T, [&]() { gm::cta_main<false>(P, big + w.W, big + w.Bi, small.data(), &slot, ring, bars); }, shuffle_order != 0);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return -1;

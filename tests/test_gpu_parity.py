@@ -108,18 +108,29 @@ def test_every_tier_matches_oracle():
     o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads())
     assert (g["status"] == o["status"]).all()
     assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
-    gm.set_options(no_tma_ring=True)   # tier 3 with plain loads instead of the TMA staging ring
     try:
+        gm.set_options(force_tier=4)                     # W and Bi in HBM (m < 384: plain loads)
         g2 = gm.simplex_batch(c, A, b)
+        assert (g2["status"] == o["status"]).all() and _close(g2["x"], o["x"])
     finally:
         gm.set_options()
-    assert (g2["status"] == o["status"]).all() and _close(g2["x"], o["x"])
+    # long rows: tier 4 streams W / Bi through the TMA staging ring; same answers with the ring disabled
+    c4, A4, b4 = feasible_bounded_lp(rng, 400, 520, 2)
+    g4 = gm.simplex_batch(c4, A4, b4)
+    assert gm.last_timing()["tier"] == 4 and (g4["status"] == S.GM_OK).all()
+    assert np.abs(np.einsum("kij,kj->ki", A4, g4["x"]) - b4).max() < 1e-7 and g4["x"].min() >= -1e-9
+    try:
+        gm.set_options(no_tma_ring=True)
+        g5 = gm.simplex_batch(c4, A4, b4)
+    finally:
+        gm.set_options()
+    assert (g5["status"] == S.GM_OK).all() and _close(g5["optF"], g4["optF"]) and _close(g5["x"], g4["x"], 1e-7)
     c, A, b = feasible_bounded_lp(rng, 16, 40, 32)
     c2, A2, b2 = raw_lp(rng, 9, 17, 64, 0.2)
     o = oracle.simplex_batch(c, A, b)
     o2 = oracle.simplex_batch(c2, A2, b2, max_pivots=20000)
     try:
-        for tier in (1, 2, 3, 4):
+        for tier in (1, 2, 3, 4, 5):
             gm.set_options(force_tier=tier)
             g = gm.simplex_batch(c, A, b)
             assert gm.last_timing()["tier"] == tier
