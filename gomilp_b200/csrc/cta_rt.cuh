@@ -38,6 +38,8 @@ GM_DEV unsigned gm_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_
 GM_DEV void gm_mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(count) : "memory");
 }
+// orders this thread's earlier generic-proxy writes (st.global / st.shared) before later async-proxy (TMA) accesses
+GM_DEV void gm_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 GM_DEV void gm_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 GM_DEV void gm_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gm_smem_u32(bar)), "r"(bytes) : "memory");

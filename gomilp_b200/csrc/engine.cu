@@ -176,6 +176,7 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
             if (ns < 2 || g.opt.reserved == 1) ns = 0;  // options.reserved = 1 disables the ring (A/B measurements)
             P.ring_stages = ns;
             P.ring_stage_bytes = ns ? (int)stage : 0;
+            P.stream_min_m = 384;
             smem = w2.small_bytes + (size_t)ns * stage;
             auto kern = simplex_wave_hbm<kHbmThreads>;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -54,6 +54,7 @@ struct BatchParams {
     int max_pivots;       // safety cap (the reference has none); <=0: 50*(m+n)+1000
     int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100 (HBM tiers: max(100, 2m))
     int ring_stages, ring_stage_bytes;  // HBM tier: TMA staging ring in shared memory (0: none)
+    int stream_min_m;                   // rows shorter than this use plain loads (bulk copies pay off for long rows)
     int hbm_layout;       // 1: W / Bi live in HBM (row strides padded to 32 B instead of to an odd count)
     // ---- outputs --------------------------------------------------------------------------------
     int* status;        // [count] gm_status
@@ -163,7 +164,7 @@ struct SolverT {
     // HBM tier: ring of shared-memory stages fed by TMA bulk copies (nullptr: plain loads)
     double* ring;
     unsigned long long* ring_bar;
-    int ring_stage_doubles, ring_ns, ring_uses;
+    int ring_stage_doubles, ring_ns, ring_uses, stream_min_m;
     int* sel;  // row list of the current stream (aliases inb: the flags are dead inside the main loop)
     bool w_loaded;   // REG tier: W holds [A | art] in ORIGINAL column order for the current LP
     // counters (uniform across the CTA)
@@ -1022,7 +1023,7 @@ struct SolverT {
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
         if constexpr (REG) return main_loop_reg(tol, phase, fresh);
-        if (ring != nullptr && m >= 384 && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
+        if (ring != nullptr && m >= stream_min_m && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
             ((m + 1) & ~1) <= ring_stage_doubles)
             return main_loop_stream(tol, phase, fresh);
         const int t = gm_tid(), T = gm_nthreads();
@@ -1278,6 +1279,9 @@ struct SolverT {
                     gm_bulk_g2s(st + (size_t)u * wcols, M + (size_t)sel[first + u] * ld + c0, row_bytes, ring_bar + sidx);
             }
         };
+        // W / Bi rows were last written with ordinary stores: make them visible to the TMA (async proxy) first
+        gm_fence_proxy_async();
+        gm_sync();
         const int pre = ntiles < ring_ns ? ntiles : ring_ns;
         for (int k = 0; k < pre; ++k) issue(k);
         bool ok = true;
@@ -1697,6 +1701,7 @@ struct SolverT {
                                double* ring_base = nullptr, unsigned long long* bars = nullptr) {
         ring = ring_base; ring_bar = bars; ring_ns = P.ring_stages; ring_stage_doubles = P.ring_stage_bytes / 8;
         ring_uses = 0;
+        stream_min_m = P.stream_min_m;
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
         const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0);

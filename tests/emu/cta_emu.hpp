@@ -264,6 +264,7 @@ inline double gm_ldg(const double* p) { return *p; }
 // copies outrun expect_tx), bit 63 = current phase parity.
 inline void gm_mbar_init(unsigned long long* bar, int) { *bar = 0; }
 inline void gm_mbar_fence_init() {}
+inline void gm_fence_proxy_async() {}
 inline void emu_mbar_add(unsigned long long* bar, long long delta, bool is_expect) {
     long long pending = (long long)(int)(unsigned)(*bar & 0xffffffffull);
     unsigned long long phase = *bar >> 63;
