@@ -160,6 +160,7 @@ struct SolverT {
     double breg[REG ? 16 : 1];
     int ncols, nn;  // current width of W and number of non-basic columns
     int wrows, vlen;  // rows of W incl. zero padding; length of the m-vectors incl. zero padding
+    double cscale;   // max |cost| of the current phase: reduced costs below 1e-9 * cscale in magnitude are noise
     double anorm_w;  // norm of the basis at its last inversion, scale of the polish residual test
     // HBM tier: ring of shared-memory stages fed by TMA bulk copies (nullptr: plain loads)
     double* ring;
@@ -477,6 +478,9 @@ struct SolverT {
             cn[k] = phase1 ? (v == n ? 1.0 : 0.0) : src_c(v);
         }
         gm_sync();
+        cscale = phase1 ? 1.0 : block_max(m > nn ? m : nn, [&](int i) {
+            return fmax(i < m ? fabs(cb[i]) : 0.0, i < nn ? fabs(cn[i]) : 0.0);
+        });
     }
 
     // physical column of W that holds basis position p / non-basic position k
@@ -1033,7 +1037,9 @@ struct SolverT {
             // r = cn - an^T y  (:236-243)
             matvec_t(r, cn, -1.0, W + m, ldw, m, nn, y);
             MinLoc rl = block_argmin(nn, [&](int k) { return r[k]; });
-            if (rl.v >= -tol || rl.v != rl.v) {  // :247-250 (a NaN-only r also ends the loop, via the polish)
+            // A reduced cost that is negative only at noise level must be judged with fresh-quality duals, as the
+            // reference does every iteration (simplex.go:236): polish first, then decide.
+            if (rl.v >= -tol || rl.v != rl.v || (!fresh && rl.v > -1e-9 * cscale)) {  // :247-250
                 if (!fresh) {  // confirm optimality with fresh-quality xb and y
                     const int rc = polish();
                     if (rc != GM_OK) return rc;
@@ -1153,7 +1159,7 @@ struct SolverT {
             bestv = red[lane & (nw - 1)];
             besti = redi[lane & (nw - 1)];
             warp_argmin(bestv, besti);
-            if (besti == INT_MAX || bestv >= -tol) {
+            if (besti == INT_MAX || bestv >= -tol || (!fresh && bestv > -1e-9 * cscale)) {
                 store_state();
                 if (!fresh) {
                     const int rc = polish();
@@ -1364,7 +1370,7 @@ struct SolverT {
                 gm_sync();
             }
             MinLoc rl = block_argmin(nn, [&](int k) { return r[k]; });
-            if (rl.v >= -tol || rl.v != rl.v) {
+            if (rl.v >= -tol || rl.v != rl.v || (!fresh && rl.v > -1e-9 * cscale)) {
                 if (!fresh) {
                     const int rc = polish();
                     if (rc != GM_OK) return rc;

@@ -114,17 +114,29 @@ def test_every_tier_matches_oracle():
         assert (g2["status"] == o["status"]).all() and _close(g2["x"], o["x"])
     finally:
         gm.set_options()
-    # long rows: tier 4 streams W / Bi through the TMA staging ring; same answers with the ring disabled
-    c4, A4, b4 = feasible_bounded_lp(rng, 400, 520, 2)
+    # long rows: tier 4 streams W / Bi through the TMA staging ring; same answers with the ring disabled, and the
+    # objective HiGHS finds. Slack form [R I] x = b, b > 0: non-degenerate, the slack basis is feasible.
+    from scipy.optimize import linprog
+    m4, n4 = 400, 700
+    A4 = np.zeros((2, m4, n4))
+    A4[:, :, : n4 - m4] = rng.random((2, m4, n4 - m4))
+    A4[:, :, n4 - m4:] = np.eye(m4)
+    b4 = 1.0 + rng.random((2, m4))
+    c4 = np.zeros((2, n4))
+    c4[:, : n4 - m4] = -rng.random((2, n4 - m4))
     g4 = gm.simplex_batch(c4, A4, b4)
     assert gm.last_timing()["tier"] == 4 and (g4["status"] == S.GM_OK).all()
-    assert np.abs(np.einsum("kij,kj->ki", A4, g4["x"]) - b4).max() < 1e-7 and g4["x"].min() >= -1e-9
+    assert np.abs(np.einsum("kij,kj->ki", A4, g4["x"]) - b4).max() < 1e-9 and g4["x"].min() >= -1e-12
+    for k in range(2):
+        hs = linprog(c4[k], A_eq=A4[k], b_eq=b4[k], bounds=(0, None), method="highs")
+        assert hs.status == 0 and abs(hs.fun - g4["optF"][k]) <= 1e-7 * max(1.0, abs(hs.fun))
     try:
         gm.set_options(no_tma_ring=True)
         g5 = gm.simplex_batch(c4, A4, b4)
     finally:
         gm.set_options()
     assert (g5["status"] == S.GM_OK).all() and _close(g5["optF"], g4["optF"]) and _close(g5["x"], g4["x"], 1e-7)
+    assert (g5["pivots"] == g4["pivots"]).all()
     c, A, b = feasible_bounded_lp(rng, 16, 40, 32)
     c2, A2, b2 = raw_lp(rng, 9, 17, 64, 0.2)
     o = oracle.simplex_batch(c, A, b)
