@@ -8,8 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libgomilp_b200.so")
-SOURCES = ["engine.cu", "bnb_host.cpp"]
-HEADERS = ["simplex_cta.cuh", "cta_rt.cuh", os.path.join("..", "..", "include", "gomilp_b200.h"),
+SOURCES = ["engine.cu", "kernels_reg.cu", "kernels_generic.cu", "bnb_host.cpp"]
+HEADERS = ["simplex_cta.cuh", "cta_rt.cuh", "kernels.h", os.path.join("..", "..", "include", "gomilp_b200.h"),
            os.path.join("..", "..", "include", "gomilp_status.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -29,15 +29,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB_PATH] + srcs
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    # the two kernel translation units dominate (minutes of cicc each: the solver is one fully inlined function per
+    # tier family), so every source is compiled to an object in its own nvcc process, in parallel, then linked
+    procs, objs, logs = [], [], []
+    for src in srcs:
+        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    ok = True
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        logs.append(" ".join(cmd) + "\n" + out)
+        ok = ok and pr.returncode == 0
+    if ok:
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        logs.append(" ".join(cmd) + "\n" + res.stdout)
+        ok = res.returncode == 0
     log = os.path.join(OUT_DIR, "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout)
-    if verbose or res.returncode != 0:
-        print(res.stdout)
-    if res.returncode != 0:
+        f.write("\n".join(logs))
+    if verbose or not ok:
+        print("\n".join(logs))
+    if not ok:
         raise RuntimeError("nvcc failed; see " + log)
     return LIB_PATH
 

@@ -49,7 +49,7 @@ WAVE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_dou
 
 EXPORTS = ["gm_device_count", "gm_init", "gm_shutdown", "gm_last_error", "gm_last_timing", "gm_set_options",
            "gm_simplex", "gm_simplex_batch", "gm_simplex_batch_device", "gm_upload_root", "gm_free_root",
-           "gm_solve_wave", "gm_milp_solve"]
+           "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve"]
 
 
 def lib():
@@ -73,6 +73,7 @@ def lib():
     L.gm_upload_root.argtypes = [vp, vp, i64, vp, i64, i64, C.POINTER(i64)]
     L.gm_free_root.argtypes = [i64]
     L.gm_solve_wave.argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.gm_solve_wave_warm.argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.gm_milp_solve.argtypes = [i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, i32, i64, f64, vp,
                                 C.POINTER(gm_milp_result), DECISION_CB, WAVE_CB, vp]
     for name in EXPORTS:
@@ -198,8 +199,11 @@ class WaveResult:
     stats: np.ndarray
 
 
-def solve_wave(root: int, n0: int, m0: int, bvar, bsign, brhs) -> WaveResult:
-    """subProblem.solve (subproblem.go:141-187) for every node of a wave; node k has L branch rows."""
+def solve_wave(root: int, n0: int, m0: int, bvar, bsign, brhs, parent=None, warm: bool = False) -> WaveResult:
+    """subProblem.solve (subproblem.go:141-187) for every node of a wave; node k has L branch rows.
+
+    warm=True goes through gm_solve_wave_warm: the engine keeps this wave's bases / inverses in HBM, and
+    ``parent[k]`` (index into the previous warm wave on this root, -1 = cold) lets node k start from there."""
     bvar = np.ascontiguousarray(bvar, dtype=np.int32)
     nodes, L = bvar.shape
     bsign = _f64(bsign).reshape(nodes, L)
@@ -209,8 +213,13 @@ def solve_wave(root: int, n0: int, m0: int, bvar, bsign, brhs) -> WaveResult:
     x = np.zeros((nodes, n0))
     basis = np.zeros((nodes, m0 + L), dtype=np.int64)
     stats = np.zeros((nodes, 8), dtype=np.int32)
-    _check(lib().gm_solve_wave(root, nodes, L, _p(bvar), _p(bsign), _p(brhs), _p(status), _p(z), _p(x), _p(basis),
-                               _p(stats)))
+    if warm:
+        par = None if parent is None else np.ascontiguousarray(parent, dtype=np.int32)
+        _check(lib().gm_solve_wave_warm(root, nodes, L, _p(bvar), _p(bsign), _p(brhs), _p(par), _p(status), _p(z),
+                                        _p(x), _p(basis), _p(stats)))
+    else:
+        _check(lib().gm_solve_wave(root, nodes, L, _p(bvar), _p(bsign), _p(brhs), _p(status), _p(z), _p(x),
+                                   _p(basis), _p(stats)))
     return WaveResult(status, z, x, basis, stats)
 
 

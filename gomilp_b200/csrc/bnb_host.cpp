@@ -27,6 +27,7 @@ namespace {
 struct Wave {
     int64_t L = 0;
     std::vector<int64_t> id, parent;
+    std::vector<int32_t> parent_idx;  // position of the parent in the previous wave (warm start)
     std::vector<int32_t> bvar;  // [nodes][L]
     std::vector<double> bsign, brhs;
     size_t nodes() const { return id.size(); }
@@ -113,10 +114,13 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
     int panic = 0, panic_lp = 0;
     bool timed_out = false;
 
+    const bool warm = (mode & GM_BNB_WARM_START) != 0;
+    mode &= 3;
     Wave cur;
     cur.L = 0;
     cur.id.push_back(0);
     cur.parent.push_back(0);
+    cur.parent_idx.push_back(-1);
     int64_t wave_no = 0;
 
     std::vector<int32_t> status, stats;
@@ -136,8 +140,11 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
         stats.assign(count * 8, 0);
         z.assign(count, 0.0);
         x.assign(count * (size_t)n0, 0.0);
-        rc = gm_solve_wave(root, (int64_t)count, cur.L, cur.bvar.data(), cur.bsign.data(), cur.brhs.data(),
-                           status.data(), z.data(), x.data(), nullptr, stats.data());
+        rc = warm ? gm_solve_wave_warm(root, (int64_t)count, cur.L, cur.bvar.data(), cur.bsign.data(),
+                                       cur.brhs.data(), cur.parent_idx.data(), status.data(), z.data(), x.data(),
+                                       nullptr, stats.data())
+                  : gm_solve_wave(root, (int64_t)count, cur.L, cur.bvar.data(), cur.bsign.data(), cur.brhs.data(),
+                                  status.data(), z.data(), x.data(), nullptr, stats.data());
         if (rc != GM_OK) {
             gm_free_root(root);
             result->status = GM_MILP_ENGINE_ERROR;
@@ -207,6 +214,7 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
                     for (int child = 0; child < 2; ++child) {  // getChild, subproblem.go:230-259
                         next.id.push_back(++next_id);
                         next.parent.push_back(cur.id[k]);
+                        next.parent_idx.push_back((int32_t)k);
                         for (int64_t l = 0; l < cur.L; ++l) {
                             next.bvar.push_back(cur.bvar[k * cur.L + l]);
                             next.bsign.push_back(cur.bsign[k * cur.L + l]);

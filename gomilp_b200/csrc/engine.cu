@@ -12,66 +12,21 @@
 #include <vector>
 
 #include "../../include/gomilp_b200.h"
-#include "simplex_cta.cuh"
+#include "kernels.h"
 
 namespace {
 
-constexpr int kSmemThreads = 256;  // tiers 1, 2: one LP per CTA, W in shared memory
-constexpr int kHbmThreads = 512;   // tiers 3, 4: W and Bi in HBM
-
-// tier 1 (m <= 64): basis inverse in registers, W + staging tile + vectors in shared memory
-template <int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) simplex_wave_reg(gm::BatchParams P) {
-    extern __shared__ double smem[];
-    __shared__ int slot;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, true);
-    gm::cta_main<true>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
-}
-
-// tier 2: W, Bi and vectors in shared memory
-template <int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) simplex_wave_smem(gm::BatchParams P) {
-    extern __shared__ double smem[];
-    __shared__ int slot;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T);
-    gm::cta_main<false>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
-}
-
-// big part (W, Bi) in HBM, small part in shared memory
-template <int T>
-__global__ void __launch_bounds__(T, 1) simplex_wave_hbm(gm::BatchParams P) {
-    extern __shared__ __align__(128) double smem[];
-    __shared__ int slot;
-    __shared__ unsigned long long bars[8];
-    // [TMA staging ring | vectors, lists]
-    const size_t ring_doubles = (size_t)P.ring_stages * (P.ring_stage_bytes / 8);
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
-    double* base = P.work + (size_t)blockIdx.x * P.work_stride;
-    gm::cta_main<false>(P, base + w.W, base + w.Bi, smem + ring_doubles, &slot, P.ring_stages > 0 ? smem : nullptr, bars);
-}
-
-// tier 3: basis inverse + vectors in shared memory, W in HBM
-template <int T>
-__global__ void __launch_bounds__(T, 1) simplex_wave_bismem(gm::BatchParams P) {
-    extern __shared__ __align__(128) double smem[];
-    __shared__ int slot;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
-    const size_t bi_doubles = w.big_doubles - w.Bi;
-    gm::cta_main<false>(P, P.work + (size_t)blockIdx.x * P.work_stride, smem, smem + bi_doubles, &slot);
-}
-
-// everything in HBM (very large m + n)
-template <int T>
-__global__ void __launch_bounds__(T, 1) simplex_wave_hbm_all(gm::BatchParams P) {
-    __shared__ int slot;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, true);
-    double* base = P.work + (size_t)blockIdx.x * P.work_stride;
-    gm::cta_main<false>(P, base + w.W, base + w.Bi, base + w.big_doubles, &slot);
-}
+using gm_kernels::kHbmThreads;
+using gm_kernels::kSmemThreads;
 
 struct Root {
     double *c = nullptr, *A = nullptr, *b = nullptr;
     int m0 = 0, n0 = 0;
+    // warm-start state: final bases / inverses of the previous wave, kept in HBM for the children
+    double* prev_bi = nullptr;
+    long long* prev_basis = nullptr;
+    int64_t prev_nodes = 0;
+    int prev_m = 0;
 };
 
 struct Engine {
@@ -142,17 +97,18 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     double* work = nullptr;
     int grid = 0, block = 0;
     size_t smem = 0;
+    P.tier = tier;
     if (tier == 1 || tier == 2) {
         block = kSmemThreads;
         smem = tier == 1 ? smem_reg : smem_all;
         int per_sm = 0;
-        auto kern = tier == 1 ? simplex_wave_reg<kSmemThreads, 2> : simplex_wave_smem<kSmemThreads, 2>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+        if (tier == 1) CK(gm_kernels::reg_prepare(smem, &per_sm));
+        else CK(gm_kernels::generic_prepare(block, smem, &per_sm));
         if (per_sm < 1) per_sm = 1;
         grid = (int)std::min<long long>(P.count, (long long)g.sms * per_sm);
         if (ev0) CK(cudaEventRecord(ev0, stream));
-        kern<<<grid, block, smem, stream>>>(P);
+        if (tier == 1) gm_kernels::reg_launch(P, grid, smem, stream);
+        else gm_kernels::generic_launch(P, grid, block, smem, stream);
     } else {
         block = kHbmThreads;
         P.hbm_layout = 1;
@@ -164,10 +120,6 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         P.work_stride = (long long)per_cta;
         if (tier == 3) {
             smem = bi_bytes + w2.small_bytes;
-            auto kern = simplex_wave_bismem<kHbmThreads>;
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (ev0) CK(cudaEventRecord(ev0, stream));
-            kern<<<grid, block, smem, stream>>>(P);
         } else if (tier == 4) {
             // TMA staging ring: up to 3 stages of 32 KB if they fit beside the vectors
             const size_t stage = 32768;
@@ -178,15 +130,13 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
             P.ring_stage_bytes = ns ? (int)stage : 0;
             P.stream_min_m = 384;
             smem = w2.small_bytes + (size_t)ns * stage;
-            auto kern = simplex_wave_hbm<kHbmThreads>;
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (ev0) CK(cudaEventRecord(ev0, stream));
-            kern<<<grid, block, smem, stream>>>(P);
         } else {
-            auto kern = simplex_wave_hbm_all<kHbmThreads>;
-            if (ev0) CK(cudaEventRecord(ev0, stream));
-            kern<<<grid, block, 0, stream>>>(P);
+            smem = 0;
         }
+        int per_sm = 0;
+        CK(gm_kernels::generic_prepare(block, smem, &per_sm));
+        if (ev0) CK(cudaEventRecord(ev0, stream));
+        gm_kernels::generic_launch(P, grid, block, smem, stream);
     }
     CK(cudaGetLastError());
     if (ev1) CK(cudaEventRecord(ev1, stream));
@@ -258,6 +208,8 @@ int gm_shutdown(void) {
         cudaFree(kv.second.c);
         cudaFree(kv.second.A);
         cudaFree(kv.second.b);
+        cudaFree(kv.second.prev_bi);
+        cudaFree(kv.second.prev_basis);
     }
     g.roots.clear();
     g.ready = false;
@@ -330,7 +282,8 @@ float ms(cudaEvent_t a, cudaEvent_t b) {
 // shared body of the host-buffer entry points: per-LP roots (stride != 0) or wave over a device root
 static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A, int64_t h_lda, const double* h_b,
                          const int64_t* h_ib, const int32_t* h_bvar, const double* h_bsign, const double* h_brhs,
-                         int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats) {
+                         int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats,
+                         long long* d_basis_keep = nullptr) {
     StreamEvents se;
     CK(se.init());
     cudaStream_t st = se.s;
@@ -370,7 +323,8 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
     CK(dF.alloc(sizeof(double) * count));
     CK(dX.alloc(sizeof(double) * count * P.x_len));
     P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.x_stride = P.x_len;
-    if (basis) { CK(dB.alloc(sizeof(int64_t) * count * m)); P.basis = dB.as<long long>(); }
+    if (d_basis_keep) P.basis = d_basis_keep;  // caller-owned device buffer (warm start keeps it for the next wave)
+    else if (basis) { CK(dB.alloc(sizeof(int64_t) * count * m)); P.basis = dB.as<long long>(); }
     if (stats) { CK(dS.alloc(sizeof(int32_t) * count * 8)); P.stats = dS.as<int>(); }
     t_timing = gm_timing{};
     int rc = launch_wave(P, st, se.e[1], se.e[2], &t_timing);
@@ -378,7 +332,7 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
     CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(optF, dF.p, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(optX, dX.p, sizeof(double) * count * P.x_len, cudaMemcpyDeviceToHost, st));
-    if (basis) CK(cudaMemcpyAsync(basis, dB.p, sizeof(int64_t) * count * m, cudaMemcpyDeviceToHost, st));
+    if (basis) CK(cudaMemcpyAsync(basis, P.basis, sizeof(int64_t) * count * m, cudaMemcpyDeviceToHost, st));
     if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * count * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(se.e[3], st));
     CK(cudaStreamSynchronize(st));
@@ -542,6 +496,8 @@ int gm_free_root(gm_root_t root) {
     cudaFree(it->second.c);
     cudaFree(it->second.A);
     cudaFree(it->second.b);
+    cudaFree(it->second.prev_bi);
+    cudaFree(it->second.prev_basis);
     g.roots.erase(it);
     return GM_OK;
 }
@@ -563,6 +519,115 @@ int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar,
     P.m0 = m0; P.n0 = n0; P.lda = n0; P.L = (int)L; P.tol = 0.0;  // subproblem.go:154,172 pass tol = 0
     P.count = (int)nodes; P.x_len = n0;
     return run_host_call(P, nullptr, nullptr, 0, nullptr, nullptr, bvar, bsign, brhs, status, z, x, basis, stats);
+}
+
+int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                       const double* brhs, const int32_t* parent, int32_t* status, double* z, double* x,
+                       int64_t* basis, int32_t* stats) {
+    int rc = ensure_ready();
+    if (rc != GM_OK) return rc;
+    if (nodes < 0 || L < 0 || nodes > INT32_MAX) return GM_ERR_BAD_SHAPE;
+    if (nodes == 0) return GM_OK;
+    if (!status || !z || !x || (L > 0 && (!bvar || !bsign || !brhs))) return GM_ERR_BAD_ARGUMENT;
+    Root* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        auto it = g.roots.find(root);
+        if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
+        r = &it->second;
+    }
+    const int m0 = r->m0, n0 = r->n0;
+    const int64_t m = m0 + L;
+    for (int64_t i = 0; i < nodes * L; ++i)
+        if (bvar[i] < 0 || bvar[i] >= n0) return GM_ERR_BAD_ARGUMENT;
+    const bool can_warm = parent && L >= 1 && r->prev_bi && r->prev_m == m - 1;
+    if (can_warm)
+        for (int64_t i = 0; i < nodes; ++i)
+            if (parent[i] >= r->prev_nodes) return GM_ERR_BAD_ARGUMENT;
+
+    StreamEvents se;
+    CK(se.init());
+    cudaStream_t st = se.s;
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c = r->c; P.A = r->A; P.b = r->b;
+    P.m0 = m0; P.n0 = n0; P.lda = n0; P.L = (int)L; P.tol = 0.0;  // subproblem.go:154,172 pass tol = 0
+    P.count = (int)nodes; P.x_len = n0; P.x_stride = n0;
+    // this wave's bases / inverses stay on the device for the next wave (if they fit comfortably)
+    double* cur_bi = nullptr;
+    long long* cur_basis = nullptr;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = (size_t)nodes * (size_t)m * (size_t)m * 8 + (size_t)nodes * (size_t)m * 8;
+    if (need < free_b / 2) {
+        CK(cudaMalloc(&cur_bi, (size_t)nodes * m * m * 8));
+        CK(cudaMalloc(&cur_basis, (size_t)nodes * m * 8));
+    }
+    DevBuf dbv(st), dbs(st), dbr(st), dpar(st), dst(st), dF(st), dX(st), dB(st), dS(st), dlist(st);
+    CK(cudaEventRecord(se.e[0], st));
+    if (L > 0) {
+        CK(dbv.alloc(sizeof(int32_t) * nodes * L));
+        CK(dbs.alloc(sizeof(double) * nodes * L));
+        CK(dbr.alloc(sizeof(double) * nodes * L));
+        CK(cudaMemcpyAsync(dbv.p, bvar, sizeof(int32_t) * nodes * L, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dbs.p, bsign, sizeof(double) * nodes * L, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dbr.p, brhs, sizeof(double) * nodes * L, cudaMemcpyHostToDevice, st));
+        P.bvar = dbv.as<int>(); P.bsign = dbs.as<double>(); P.brhs = dbr.as<double>();
+    }
+    if (can_warm) {
+        CK(dpar.alloc(sizeof(int32_t) * nodes));
+        CK(cudaMemcpyAsync(dpar.p, parent, sizeof(int32_t) * nodes, cudaMemcpyHostToDevice, st));
+        P.warm_parent = dpar.as<int>();
+        P.warm_basis = r->prev_basis;
+        P.warm_bi = r->prev_bi;
+    }
+    CK(dst.alloc(sizeof(int32_t) * nodes));
+    CK(dF.alloc(sizeof(double) * nodes));
+    CK(dX.alloc(sizeof(double) * nodes * n0));
+    CK(dS.alloc(sizeof(int32_t) * nodes * 8));
+    P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.stats = dS.as<int>();
+    if (cur_basis) P.basis = cur_basis;
+    else if (basis) { CK(dB.alloc(sizeof(int64_t) * nodes * m)); P.basis = dB.as<long long>(); }
+    P.bi_out = cur_bi;
+    t_timing = gm_timing{};
+    rc = launch_wave(P, st, se.e[1], se.e[2], &t_timing);
+    if (rc == GM_OK) {
+        CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * nodes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        t_timing.kernel_ms = ms(se.e[1], se.e[2]);
+        // nodes whose warm start died are re-solved from scratch, in place, by a second launch
+        std::vector<int> retry;
+        for (int64_t i = 0; i < nodes; ++i)
+            if (status[i] == GM_ERR_WARM_RETRY) retry.push_back((int)i);
+        if (!retry.empty()) {
+            CK(dlist.alloc(sizeof(int) * retry.size()));
+            CK(cudaMemcpyAsync(dlist.p, retry.data(), sizeof(int) * retry.size(), cudaMemcpyHostToDevice, st));
+            gm::BatchParams Q = P;
+            Q.warm_parent = nullptr;
+            Q.lp_list = dlist.as<int>();
+            Q.count = (int)retry.size();
+            rc = launch_wave(Q, st, se.e[3], se.e[4], &t_timing);
+            if (rc == GM_OK) {
+                CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * nodes, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                t_timing.kernel_ms += ms(se.e[3], se.e[4]);
+            }
+        }
+    }
+    if (rc == GM_OK) {
+        CK(cudaMemcpyAsync(z, dF.p, sizeof(double) * nodes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(x, dX.p, sizeof(double) * nodes * n0, cudaMemcpyDeviceToHost, st));
+        if (basis) CK(cudaMemcpyAsync(basis, P.basis, sizeof(int64_t) * nodes * m, cudaMemcpyDeviceToHost, st));
+        if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * nodes * 8, cudaMemcpyDeviceToHost, st));
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(r->prev_bi);
+    cudaFree(r->prev_basis);
+    r->prev_bi = cur_bi;
+    r->prev_basis = cur_basis;
+    r->prev_nodes = cur_bi ? nodes : 0;
+    r->prev_m = (int)m;
+    return rc;
 }
 
 }  // extern "C"

@@ -1,0 +1,22 @@
+// kernels_reg.cu — tier 1 (m <= 64): basis inverse in registers, W + staging tile + vectors in shared memory.
+#include "kernels.h"
+
+namespace {
+__global__ void __launch_bounds__(gm_kernels::kSmemThreads, 2) simplex_wave_reg(gm::BatchParams P) {
+    extern __shared__ double smem[];
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, gm_kernels::kSmemThreads, true);
+    gm::cta_main<true>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
+}
+}  // namespace
+
+namespace gm_kernels {
+cudaError_t reg_prepare(size_t smem, int* ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(simplex_wave_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_reg, kSmemThreads, smem);
+}
+void reg_launch(const gm::BatchParams& P, int grid, size_t smem, cudaStream_t st) {
+    simplex_wave_reg<<<grid, kSmemThreads, smem, st>>>(P);
+}
+}  // namespace gm_kernels

@@ -49,12 +49,19 @@ struct BatchParams {
     const double* bsign;  // [count][L] gsharp[var] = +1 / -1
     const double* brhs;   // [count][L] hsharp
     const long long* initial_basic;  // [count][m] or nullptr (simplex.go:147-160)
+    // Warm start of B&B children (north star "children warm-start from the parent basis"): node k continues from
+    // node warm_parent[k] of the PREVIOUS wave (depth L-1), whose final basis / inverse are kept in HBM.
+    const int* warm_parent;          // [count] index into the previous wave, -1 = cold start; nullptr = all cold
+    const long long* warm_basis;     // [prev_count][m-1]
+    const double* warm_bi;           // [prev_count][(m-1)*(m-1)] row-major basis inverses of the previous wave
+    double* bi_out;                  // [count][m*m] or nullptr: final basis inverse of every node (for the next wave)
     double tol;
     int count;
     int max_pivots;       // safety cap (the reference has none); <=0: 50*(m+n)+1000
     int refactor_period;  // pivots between Gauss-Jordan rebuilds of Bi; <=0: 100 (HBM tiers: max(100, 2m))
     int ring_stages, ring_stage_bytes;  // HBM tier: TMA staging ring in shared memory (0: none)
     int stream_min_m;                   // rows shorter than this use plain loads (bulk copies pay off for long rows)
+    int tier;             // 1..5, see gm_timing.tier (selects where the generic kernel finds W / Bi / vectors)
     int hbm_layout;       // 1: W / Bi live in HBM (row strides padded to 32 B instead of to an odd count)
     // ---- outputs --------------------------------------------------------------------------------
     int* status;        // [count] gm_status
@@ -69,6 +76,7 @@ struct BatchParams {
     double* work;           // HBM workspace for the tiers that need one: [gridDim][work_stride]
     long long work_stride;  // doubles per CTA
     int* queue;             // work-queue counter (zeroed before launch)
+    const int* lp_list;     // optional: work item k solves LP lp_list[k] (retry launches); nullptr = identity
 };
 
 // Workspace of one CTA, split in a "big" part (W and Bi: O(mn) doubles) and a "small" part (vectors,
@@ -845,6 +853,9 @@ struct SolverT {
             return (i < m ? fabs(cb[i]) + anorm_w * fabs(y[i]) : 0.0) + (i < nn ? fabs(cn[i]) : 0.0);
         }) + 1e-300;
         if (rb <= 1e-13 * sb && rc <= 1e-13 * sc) return GM_OK;
+#ifdef GM_DEBUG_EMU
+        if (t == 0) printf("polish -> reinversion: rb=%g sb=%g rc=%g sc=%g pivots=%d\n", rb, sb, rc, sc, piv1 + piv2);
+#endif
         double cond1;
         if (invert_basis(&cond1)) return GM_ERR_CONDITION;
         recompute_xb_y();
@@ -1498,12 +1509,42 @@ struct SolverT {
         return GM_OK;
     }
 
+    // ---- warm start: parent's optimal basis plus the slack of the new branch row ------------------------
+    // B' = [B 0; g 1] with g = the new row restricted to the basic columns (one entry, +-1, at the branched
+    // variable if it is basic), so B'^-1 = [B^-1 0; -g B^-1 1] is read off the parent's inverse without any
+    // factorisation. The child is primal infeasible in the new row only; Phase I / II then need a few pivots.
+    GM_DEV bool warm_start(const BatchParams& P, int lp) {
+        const int t = gm_tid(), T = gm_nthreads();
+        if (!P.warm_parent || L < 1) return false;
+        const int par = P.warm_parent[lp];
+        if (par < 0) return false;
+        const int mp = m - 1;
+        const long long* pb = P.warm_basis + (size_t)par * mp;
+        const double* pbi = P.warm_bi + (size_t)par * mp * mp;
+        const int bad = block_min_int(mp, [&](int p) { return (pb[p] < 0 || pb[p] >= n - 1) ? p : INT_MAX; });
+        if (bad != INT_MAX) return false;
+        for (int p = t; p < mp; p += T) basic[p] = (int)pb[p];
+        if (t == 0) basic[mp] = n - 1;
+        gm_sync();
+        const int bv_new = bvar[L - 1];
+        const double sg = bsign[L - 1];
+        const int pstar = block_min_int(mp, [&](int p) { return basic[p] == bv_new ? p : INT_MAX; });
+        build_w(n, false);
+        bi_fill([&](int i, int j) {
+            if (i < mp) return j < mp ? pbi[(size_t)i * mp + j] : 0.0;
+            if (j == mp) return 1.0;
+            return pstar == INT_MAX ? 0.0 : -sg * pbi[(size_t)pstar * mp + j];
+        });
+        anorm_w = 1.0;
+        return true;
+    }
+
     // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
-    GM_DEV int find_initial_basic(bool& fresh) {
+    GM_DEV int find_initial_basic(bool& fresh, bool warm) {
         const int t = gm_tid(), T = gm_nthreads();
         double cond1 = 0;
-        fresh = true;
-        bool have = try_permutation_basis();
+        fresh = !warm;  // an inherited inverse is polished before it is trusted for an optimality verdict
+        bool have = warm || try_permutation_basis();
         if (!have) {
             // optimistic: the reverse scan accepts the last m columns whenever that block is comfortably
             // conditioned (every leading sub-block is then at least as well conditioned in the 2-norm)
@@ -1603,7 +1644,7 @@ struct SolverT {
         w_loaded = false;
         int status = GM_OK;
         double optF = NAN;
-        bool have_x = false, have_basis = false;
+        bool have_x = false, have_basis = false, ran_main = false;
 
         // every padded vector starts as zeros (REG tier reads up to 64 entries)
         for (int i = t; i < vlen; i += T) {
@@ -1635,6 +1676,8 @@ struct SolverT {
             }
         } else {
             bool fresh = true;
+            bool have_start = false;  // basis, W, Bi, xb, y already in place (caller-supplied initialBasic)
+            bool warm = false;
             if (P.initial_basic) {  // :147-160
                 const long long* ib = P.initial_basic + (size_t)lp * m;
                 const int bad = block_min_int(m, [&](int p) { return (ib[p] < 0 || ib[p] >= n) ? p : INT_MAX; });
@@ -1659,11 +1702,23 @@ struct SolverT {
                         }
                     }
                 }
+                have_start = true;
             } else {
-                status = find_initial_basic(fresh);
+                warm = warm_start(P, lp);
             }
+            if (!have_start) status = find_initial_basic(fresh, warm);
             if (status == GM_OK) {
                 status = main_loop(P.tol, 2, fresh);
+                ran_main = true;
+            }
+            // A warm start follows a different pivot path than the cold solve; if that path dies (ill-conditioned
+            // basis, Bland dead end, iteration cap, unbounded ray at noise level) the engine re-solves the node from
+            // scratch in a follow-up launch (engine.cu: gm_solve_wave_warm).
+            if (warm && status != GM_OK && status != GM_ERR_INFEASIBLE) {
+                status = GM_ERR_WARM_RETRY;
+                ran_main = false;
+            }
+            if (ran_main) {
                 if (status == GM_ERR_UNBOUNDED) {
                     optF = -INFINITY;  // :260-263
                 } else {
@@ -1689,6 +1744,19 @@ struct SolverT {
         if (P.basis) {
             long long* bo = P.basis + (size_t)lp * m;
             for (int p = t; p < m; p += T) bo[p] = have_basis ? (long long)basic[p] : -1;
+        }
+        if (P.bi_out && have_basis && status == GM_OK) {
+            double* out = P.bi_out + (size_t)lp * m * m;
+            if constexpr (REG) {
+                const int row = t >> 2, q = t & 3;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int col = 4 * jj + q;
+                    if (row < m && col < m) out[(size_t)row * m + col] = breg[jj];
+                }
+            } else {
+                for_each_2d(m, m, [&](int i, int j) { out[(size_t)i * m + j] = Bi[(size_t)i * ldb + j]; });
+            }
         }
         if (t == 0) {
             P.status[lp] = status;
@@ -1750,9 +1818,10 @@ GM_DEV void cta_main(const BatchParams& P, double* wbase, double* bibase, double
     for (;;) {
         if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
         gm_sync();
-        const int lp = *slot;
+        const int item = *slot;
         gm_sync();
-        if (lp >= P.count) break;
+        if (item >= P.count) break;
+        const int lp = P.lp_list ? P.lp_list[item] : item;
         s.bind_lp(P, lp);
         s.solve(P, lp);
     }

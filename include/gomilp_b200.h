@@ -92,6 +92,17 @@ int gm_free_root(gm_root_t root);
 int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
                   const double* brhs, int32_t* status, double* z, double* x, int64_t* basis, int32_t* stats);
 
+/* Warm-started wave (north star: "children warm-start from the parent basis"). Same as gm_solve_wave, plus
+ * parent[k] = index of node k's parent in the PREVIOUS gm_solve_wave_warm call on this root (which must have had
+ * depth L-1), or -1 for a cold start; parent == NULL = all cold. The engine keeps every node's final basis and
+ * basis inverse of the last warm wave in HBM (nodes x (m^2 + m) x 8 B; skipped when it would not fit), and a child
+ * starts from [B 0; g 1]^-1 = [B^-1 0; -g B^-1 1] without any factorisation. Optimal objective and x are those of
+ * the cold solve whenever the optimum is unique; the pivot path differs, so this is not a replay of lp.Simplex's
+ * initialBasic = nil call (subproblem.go:154) and is off by default in gm_milp_solve. */
+int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                       const double* brhs, const int32_t* parent, int32_t* status, double* z, double* x,
+                       int64_t* basis, int32_t* stats);
+
 /* ---- (3) whole MILP: milpProblem.solve, ilp.go:75-116 ------------------------------------------- */
 typedef struct gm_milp_result {
     int32_t status;     /* gm_milp_status */
@@ -112,7 +123,7 @@ typedef void (*gm_decision_cb)(void* user, int64_t id, int64_t parent, int32_t d
 typedef void (*gm_wave_cb)(void* user, int64_t wave, int64_t nodes, int64_t pivots, double kernel_ms);
 
 /* c [nvar]; A [meq][nvar], b [meq] (meq may be 0); G [nineq][nvar], h [nineq] (nineq may be 0);
- * integrality [nvar] (0/1). heuristic: gm_branch_heuristic; mode: gm_bnb_mode.
+ * integrality [nvar] (0/1). heuristic: gm_branch_heuristic; mode: gm_bnb_mode, optionally | GM_BNB_WARM_START.
  * node_limit / time_limit_s stand in for the context deadline (0 = none).
  * x must hold nvar + nineq + 1 doubles. */
 int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const double* A, const double* b, int64_t nineq,

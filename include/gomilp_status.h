@@ -36,7 +36,8 @@ typedef enum gm_status {
     GM_ERR_TOO_LARGE = 67,       /* shape exceeds what the selected kernel tier supports */
     GM_ERR_ITERATION_LIMIT = 68, /* safety cap hit (the reference has none and would spin) */
     GM_ERR_BAD_HANDLE = 69,
-    GM_ERR_BAD_ARGUMENT = 70
+    GM_ERR_BAD_ARGUMENT = 70,
+    GM_ERR_WARM_RETRY = 71       /* internal: a warm-started node must be re-solved cold (never returned to callers) */
 } gm_status;
 
 /* Tolerances of the reference, simplex.go:42-58 and the call sites that hard-wire them. */
@@ -85,6 +86,9 @@ typedef enum gm_branch_heuristic {
  * index). FIXED propagates the heuristic and evaluates it on the fractional integer variables of x
  * so that trees terminate; it exists for throughput runs and has no reference counterpart. */
 typedef enum gm_bnb_mode { GM_BNB_COMPAT = 0, GM_BNB_FIXED = 1 } gm_bnb_mode;
+/* OR-ed into `mode`: children start from their parent's optimal basis (gm_solve_wave_warm) instead of from
+ * scratch. Same optima where they are unique, far fewer pivots; not a pivot-for-pivot replay of the reference. */
+#define GM_BNB_WARM_START 4
 
 #ifdef __cplusplus
 }

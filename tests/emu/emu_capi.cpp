@@ -6,16 +6,39 @@
 #include "cta_emu.hpp"
 #include "../../gomilp_b200/csrc/simplex_cta.cuh"
 
+static const int* g_emu_lp_list = nullptr;  // retry launches: work item k solves LP list[k]
+
 extern "C" {
 
 // Same meaning as the device batch entry: `count` LPs, shared (stride 0) or per-LP roots, optional
 // branch rows. T = emulated threads per CTA (power of two, multiple of 32).
+int emu_simplex_batch_ex(int count, const double* c, const double* A, const double* b, long long c_stride,
+                         long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
+                         const double* bsign, const double* brhs, const long long* initial_basic, double tol,
+                         int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
+                         int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg, int ring_stages,
+                         int ring_stage_bytes, const int* warm_parent, const long long* warm_basis,
+                         const double* warm_bi, double* bi_out);
+
 int emu_simplex_batch(int count, const double* c, const double* A, const double* b, long long c_stride,
                       long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
                       const double* bsign, const double* brhs, const long long* initial_basic, double tol,
                       int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
                       int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg, int ring_stages,
                       int ring_stage_bytes) {
+    return emu_simplex_batch_ex(count, c, A, b, c_stride, A_stride, b_stride, lda, m0, n0, L, bvar, bsign, brhs,
+                                initial_basic, tol, max_pivots, refactor_period, status, optF, x, x_stride, x_len, basis,
+                                stats, T, shuffle_order, reg, ring_stages, ring_stage_bytes, nullptr, nullptr, nullptr,
+                                nullptr);
+}
+
+int emu_simplex_batch_ex(int count, const double* c, const double* A, const double* b, long long c_stride,
+                         long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
+                         const double* bsign, const double* brhs, const long long* initial_basic, double tol,
+                         int max_pivots, int refactor_period, int* status, double* optF, double* x, long long x_stride,
+                         int x_len, long long* basis, int* stats, int T, int shuffle_order, int reg, int ring_stages,
+                         int ring_stage_bytes, const int* warm_parent, const long long* warm_basis,
+                         const double* warm_bi, double* bi_out) {
     gm::BatchParams P;
     std::memset(&P, 0, sizeof(P));
     P.c = c; P.A = A; P.b = b;
@@ -26,6 +49,8 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
     P.tol = tol; P.count = count; P.max_pivots = max_pivots; P.refactor_period = refactor_period;
     P.status = status; P.optF = optF; P.x = x; P.x_stride = x_stride; P.x_len = x_len;
     P.basis = basis; P.stats = stats;
+    P.warm_parent = warm_parent; P.warm_basis = warm_basis; P.warm_bi = warm_bi; P.bi_out = bi_out;
+    P.lp_list = g_emu_lp_list;
     int queue = 0;
     P.queue = &queue;
     if (reg && (T != 256 || m0 + L > 64)) return -2;
@@ -58,7 +83,14 @@ int emu_simplex_batch(int count, const double* c, const double* A, const double*
 #include "../../include/gomilp_b200.h"
 
 namespace {
-struct EmuRoot { std::vector<double> c, A, b; int m0, n0; };
+struct EmuRoot {
+    std::vector<double> c, A, b;
+    int m0, n0;
+    std::vector<double> prev_bi;
+    std::vector<long long> prev_basis;
+    int64_t prev_nodes = 0;
+    int prev_m = 0;
+};
 std::map<gm_root_t, EmuRoot> g_roots;
 gm_root_t g_next = 1;
 int g_T = 64;
@@ -91,6 +123,40 @@ int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar,
                                bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0,
                                reinterpret_cast<long long*>(basis), stats, g_T, 0,
                                (g_reg && r.m0 + (int)L <= 64) ? 1 : 0, 0, 0);
+    return rc == 0 ? GM_OK : GM_ERR_CUDA;
+}
+int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
+                       const double* brhs, const int32_t* parent, int32_t* status, double* z, double* x, int64_t* basis,
+                       int32_t* stats) {
+    auto it = g_roots.find(root);
+    if (it == g_roots.end()) return GM_ERR_BAD_HANDLE;
+    EmuRoot& r = it->second;
+    const int64_t m = r.m0 + L;
+    std::vector<double> cur_bi((size_t)nodes * m * m, 0.0);
+    std::vector<long long> cur_basis((size_t)nodes * m, -1);
+    const bool can_warm = parent && L >= 1 && r.prev_nodes > 0 && r.prev_m == m - 1;
+    const bool reg = g_reg && m <= 64;
+    int rc = emu_simplex_batch_ex((int)nodes, r.c.data(), r.A.data(), r.b.data(), 0, 0, 0, r.n0, r.m0, r.n0, (int)L, bvar,
+                                  bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0, cur_basis.data(), stats,
+                                  reg ? 256 : g_T, 0, reg ? 1 : 0, 0, 0, can_warm ? parent : nullptr,
+                                  can_warm ? r.prev_basis.data() : nullptr, can_warm ? r.prev_bi.data() : nullptr,
+                                  cur_bi.data());
+    // nodes whose warm start died are re-solved cold in place (engine.cu does the same with a second launch)
+    std::vector<int> retry;
+    for (int64_t i = 0; i < nodes; ++i)
+        if (status[i] == GM_ERR_WARM_RETRY) retry.push_back((int)i);
+    if (rc == 0 && !retry.empty()) {
+        g_emu_lp_list = retry.data();
+        rc = emu_simplex_batch_ex((int)retry.size(), r.c.data(), r.A.data(), r.b.data(), 0, 0, 0, r.n0, r.m0, r.n0, (int)L,
+                                  bvar, bsign, brhs, nullptr, 0.0, 0, 0, status, z, x, r.n0, r.n0, cur_basis.data(), stats,
+                                  reg ? 256 : g_T, 0, reg ? 1 : 0, 0, 0, nullptr, nullptr, nullptr, cur_bi.data());
+        g_emu_lp_list = nullptr;
+    }
+    if (basis) std::memcpy(basis, cur_basis.data(), sizeof(long long) * cur_basis.size());
+    r.prev_bi.swap(cur_bi);
+    r.prev_basis.swap(cur_basis);
+    r.prev_nodes = nodes;
+    r.prev_m = (int)m;
     return rc == 0 ? GM_OK : GM_ERR_CUDA;
 }
 }  // extern "C"

@@ -260,3 +260,22 @@ def test_sharded_driver_single_rank():
     g = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED,
                       heuristic=S.GM_BRANCH_MOST_INFEASIBLE, node_limit=500)
     assert r.status == g.status and r.nodes == g.nodes and (r.z == g.z or (r.x is None and g.x is None))
+
+
+@pytest.mark.timeout(300)
+def test_warm_started_children_reach_the_cold_optimum():
+    rng = np.random.default_rng(41)
+    ratio = []
+    for _ in range(8):
+        p = random_milp(rng, int(rng.integers(4, 10)), int(rng.integers(2, 5)))
+        cold = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, heuristic=1,
+                             node_limit=2000)
+        warm = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                             mode=S.GM_BNB_FIXED | S.GM_BNB_WARM_START, heuristic=1, node_limit=2000)
+        assert warm.status == cold.status
+        if cold.status == S.GM_MILP_OK:
+            assert abs(warm.z - cold.z) <= RTOL * max(1.0, abs(cold.z))
+        if warm.nodes == cold.nodes and cold.nodes > 1:
+            ratio.append(cold.pivots / max(1, warm.pivots))
+    print("cold / warm pivots on identical trees:", [round(r, 2) for r in ratio])
+    assert ratio and min(ratio) >= 1.0

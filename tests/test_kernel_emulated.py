@@ -135,3 +135,24 @@ def test_emulated_bnb_replays_oracle_decisions():
         if g["status"] == S.GM_MILP_OK and o.status == S.GM_MILP_OK:
             assert abs(g["z"] - o.z) <= 1e-9 * max(1.0, abs(o.z))
     assert same >= 3
+
+
+@pytest.mark.parametrize("reg", [False, True])
+def test_emulated_warm_started_children_reach_the_cold_optimum(reg):
+    """GM_BNB_WARM_START: children continue from [B 0; g 1]^-1 built from the parent's inverse. Same optimum,
+    same tree where the LP optima are unique, fewer pivots."""
+    rng = np.random.default_rng(33)
+    fewer = 0
+    for _ in range(4):
+        p = random_milp(rng, int(rng.integers(3, 7)), 3)
+        cold = E.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=1, heuristic=1, node_limit=60,
+                            T=64, reg=reg)
+        warm = E.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=1 | S.GM_BNB_WARM_START,
+                            heuristic=1, node_limit=60, T=64, reg=reg)
+        assert warm["status"] == cold["status"]
+        if cold["status"] == S.GM_MILP_OK:
+            assert abs(warm["z"] - cold["z"]) <= 1e-9 * max(1.0, abs(cold["z"]))
+            assert _close(warm["x"], cold["x"])
+        if warm["nodes"] == cold["nodes"] and cold["nodes"] > 1:
+            fewer += int(warm["pivots"] < cold["pivots"])
+    assert fewer >= 1
