@@ -15,6 +15,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+INC = os.path.join("..", "..", "include")
+DEPS = {
+    "engine.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_b200.h"),
+                  os.path.join(INC, "gomilp_status.h")],
+    "kernels_reg.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
+    "kernels_generic.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
+    "bnb_host.cpp": [os.path.join(INC, "gomilp_b200.h"), os.path.join(INC, "gomilp_status.h")],
+}
+
+
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in [src] + DEPS.get(src, []))
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -36,6 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in srcs:
         obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
+        if not force and not _obj_stale(src, obj):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
@@ -59,4 +78,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -33,10 +33,15 @@ struct Wave {
     size_t nodes() const { return id.size(); }
 };
 
-// tree.go:276-297
-bool feasible_for_ip(const uint8_t* integ, const double* x, int64_t n) {
+// tree.go:276-297: exact x == trunc(x). itol > 0 (warm-start mode only, which is not a replay) accepts values
+// within itol of an integer: a warm-started x carries 1e-16-level noise that the exact test would branch on forever.
+bool is_integral(double v, double itol) {
+    if (itol <= 0.0) return v == std::trunc(v);
+    return std::fabs(v - std::nearbyint(v)) <= itol;
+}
+bool feasible_for_ip(const uint8_t* integ, const double* x, int64_t n, double itol) {
     for (int64_t i = 0; i < n; ++i)
-        if (integ[i] && x[i] != std::trunc(x[i])) return false;
+        if (integ[i] && !is_integral(x[i], itol)) return false;
     return true;
 }
 
@@ -51,19 +56,19 @@ int64_t maxfun_point(const double* c, const uint8_t* integ, int64_t n) {
 
 // FIXED mode (gm_bnb_mode): heuristics evaluated on the fractional integer variables of x.
 int64_t fixed_point(int heuristic, const double* c, const double* x, const uint8_t* integ, int64_t n,
-                    int64_t last_var) {
+                    int64_t last_var, double itol) {
     if (heuristic == GM_BRANCH_NAIVE) {
         const int64_t start = last_var < 0 ? 0 : (last_var + 1) % n;
         for (int64_t k = 0; k < n; ++k) {
             const int64_t i = (start + k) % n;
-            if (integ[i] && x[i] != std::trunc(x[i])) return i;
+            if (integ[i] && !is_integral(x[i], itol)) return i;
         }
         return -1;
     }
     int64_t best = -1;
     double bestv = -1;
     for (int64_t i = 0; i < n; ++i) {
-        if (!integ[i] || x[i] == std::trunc(x[i])) continue;
+        if (!integ[i] || is_integral(x[i], itol)) continue;
         double score;
         if (heuristic == GM_BRANCH_MOST_INFEASIBLE) {
             const double f = x[i] - std::floor(x[i]);
@@ -115,6 +120,7 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
     bool timed_out = false;
 
     const bool warm = (mode & GM_BNB_WARM_START) != 0;
+    const double itol = warm ? 1e-9 : 0.0;
     mode &= 3;
     Wave cur;
     cur.L = 0;
@@ -177,7 +183,7 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
                     panic_lp = st;
                     break;
                 }
-                if (feasible_for_ip(integ.data(), xk, n0)) {  // tree.go:88-92
+                if (feasible_for_ip(integ.data(), xk, n0, itol)) {  // tree.go:88-92
                     if (on_decision)
                         on_decision(user, 0, 0, 0, st, zk, GM_DEC_INITIAL_RX_FEASIBLE_FOR_IP, -1, 0.0);
                     have_inc = true;
@@ -194,7 +200,7 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
             } else if (incumbent_z <= zk) {
                 decision = GM_DEC_WORSE_THAN_INCUMBENT;
             } else if (incumbent_z > zk) {
-                if (feasible_for_ip(integ.data(), xk, n0)) {
+                if (feasible_for_ip(integ.data(), xk, n0, itol)) {
                     have_inc = true;
                     inc_z = zk;
                     inc_x.assign(xk, xk + n0);
@@ -207,7 +213,7 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
                         on = maxfun_point(c0.data(), integ.data(), n0);
                     } else {
                         const int64_t last = cur.L > 0 ? cur.bvar[k * cur.L + cur.L - 1] : -1;
-                        on = fixed_point(heuristic, c0.data(), xk, integ.data(), n0, last);
+                        on = fixed_point(heuristic, c0.data(), xk, integ.data(), n0, last, itol);
                         if (on < 0) on = maxfun_point(c0.data(), integ.data(), n0);
                     }
                     const double fl = std::floor(xk[on]);
