@@ -18,8 +18,12 @@ rep, kname = sys.argv[1], sys.argv[2]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "gomilp_b200/_build/libgomilp_b200.so")], cwd=tmp,
                check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in glob.glob(os.path.join(tmp, "*.cubin")) if "bnb_host" not in f][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True).stdout.split("\n")
+dis = []
+for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
+    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True).stdout
+    if kname in out:
+        dis = out.split("\n")
+        break
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 raw_csv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 
