@@ -2,11 +2,19 @@
 #include "kernels.h"
 
 namespace {
+// cold waves / batches (the bench path): no warm-start code in the kernel
 __global__ void __launch_bounds__(gm_kernels::kSmemThreads, 2) simplex_wave_reg(gm::BatchParams P) {
     extern __shared__ double smem[];
     __shared__ int slot;
     const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, gm_kernels::kSmemThreads, true);
-    gm::cta_main<true>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
+    gm::cta_main<true, false>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
+}
+// gm_solve_wave_warm: children start from the parent's inverse and every node writes its own back to HBM
+__global__ void __launch_bounds__(gm_kernels::kSmemThreads, 2) simplex_wave_reg_warm(gm::BatchParams P) {
+    extern __shared__ double smem[];
+    __shared__ int slot;
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, gm_kernels::kSmemThreads, true);
+    gm::cta_main<true, true>(P, smem + w.W, smem + w.Bi, smem + w.big_doubles, &slot);
 }
 }  // namespace
 
@@ -14,9 +22,12 @@ namespace gm_kernels {
 cudaError_t reg_prepare(size_t smem, int* ctas_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(simplex_wave_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(simplex_wave_reg_warm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_reg, kSmemThreads, smem);
 }
 void reg_launch(const gm::BatchParams& P, int grid, size_t smem, cudaStream_t st) {
-    simplex_wave_reg<<<grid, kSmemThreads, smem, st>>>(P);
+    if (P.warm_parent || P.bi_out) simplex_wave_reg_warm<<<grid, kSmemThreads, smem, st>>>(P);
+    else simplex_wave_reg<<<grid, kSmemThreads, smem, st>>>(P);
 }
 }  // namespace gm_kernels

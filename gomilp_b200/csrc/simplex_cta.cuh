@@ -153,7 +153,9 @@ struct MinLoc {
     int i;
 };
 
-template <bool REG>
+// WARM = compiled with the warm-start entry / basis-inverse output paths (gm_solve_wave_warm); the cold
+// instantiation of the register tier is kept free of them because they cost registers in the hot loop.
+template <bool REG, bool WARM = true>
 struct SolverT {
     // problem
     int m, n, m0, n0, L, lda;
@@ -1704,7 +1706,7 @@ struct SolverT {
                 }
                 have_start = true;
             } else {
-                warm = warm_start(P, lp);
+                if constexpr (WARM) warm = warm_start(P, lp);
             }
             if (!have_start) status = find_initial_basic(fresh, warm);
             if (status == GM_OK) {
@@ -1745,7 +1747,7 @@ struct SolverT {
             long long* bo = P.basis + (size_t)lp * m;
             for (int p = t; p < m; p += T) bo[p] = have_basis ? (long long)basic[p] : -1;
         }
-        if (P.bi_out && have_basis && status == GM_OK) {
+        if (WARM && P.bi_out && have_basis && status == GM_OK) {
             double* out = P.bi_out + (size_t)lp * m * m;
             if constexpr (REG) {
                 const int row = t >> 2, q = t & 3;
@@ -1803,10 +1805,10 @@ struct SolverT {
 };
 
 // Persistent CTA: pulls LP indices from a global counter until the batch is exhausted.
-template <bool REG>
+template <bool REG, bool WARM = true>
 GM_DEV void cta_main(const BatchParams& P, double* wbase, double* bibase, double* small,
                      int* slot /* CTA-shared int */, double* ring = nullptr, unsigned long long* bars = nullptr) {
-    SolverT<REG> s;
+    SolverT<REG, WARM> s;
     s.bind_workspace(P, wbase, bibase, small, ring, bars);
     if (ring != nullptr) {
         if (gm_tid() == 0) {
