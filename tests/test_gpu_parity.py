@@ -279,3 +279,48 @@ def test_warm_started_children_reach_the_cold_optimum():
             ratio.append(cold.pivots / max(1, warm.pivots))
     print("cold / warm pivots on identical trees:", [round(r, 2) for r in ratio])
     assert ratio and min(ratio) >= 1.0
+
+
+def test_edge_cases_empty_ragged_and_strided():
+    """Empty batch, 1x2 and 1x1 LPs, a wave of depth 0 (the root), row stride > n (mat.Dense views), odd shapes
+    on every tier boundary."""
+    import ctypes as C
+    # empty batch: nothing to do, GM_OK
+    e = gm.simplex_batch(np.zeros((0, 3)), np.zeros((0, 2, 3)), np.zeros((0, 2)))
+    assert e["status"].shape == (0,)
+    # 1 x 1 (m == n path) and 1 x 2
+    r = gm.simplex([2.0], [[4.0]], [2.0])
+    assert r.status == S.GM_OK and _close(r.x, [0.5]) and _close(r.optF, 1.0)
+    r = gm.simplex([1.0, -1.0], [[1.0, 1.0]], [3.0])
+    assert r.status == S.GM_OK and _close(r.x, [0.0, 3.0]) and _close(r.optF, -3.0)
+    # root wave (L = 0) equals the single-LP entry point
+    rng = np.random.default_rng(12)
+    c, A, b = feasible_bounded_lp(rng, 7, 15)
+    root = gm.upload_root(c, A, b)
+    try:
+        w = gm.solve_wave(root, 15, 7, np.zeros((1, 0), dtype=np.int32), np.zeros((1, 0)), np.zeros((1, 0)))
+    finally:
+        gm.free_root(root)
+    s1 = gm.simplex(c, A, b)
+    assert w.status[0] == s1.status == S.GM_OK and _close(w.x[0], s1.x) and _close(w.z[0], s1.optF)
+    # strided A (lda > n): a column slice of a wider row-major matrix, passed without copying
+    wide = np.zeros((7, 20))
+    wide[:, :15] = A
+    L = gm.capi.lib()
+    optF = C.c_double(0.0)
+    x = np.zeros(15)
+    st = L.gm_simplex(c.ctypes.data_as(C.c_void_p), wide.ctypes.data_as(C.c_void_p), 20, b.ctypes.data_as(C.c_void_p),
+                      7, 15, 0.0, None, C.byref(optF), x.ctypes.data_as(C.c_void_p), None, None)
+    assert st == S.GM_OK and _close(x, s1.x) and _close(optF.value, s1.optF)
+    # shapes straddling the tier boundaries, checked against the oracle
+    for (m, n, k) in [(64, 200, 4), (65, 131, 4), (63, 64, 4), (97, 99, 2)]:
+        c, A, b = feasible_bounded_lp(rng, m, n, k)
+        g = gm.simplex_batch(c, A, b)
+        o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads(), max_pivots=20000)
+        ok = o["status"] == S.GM_OK
+        assert (g["status"][ok] == S.GM_OK).all()
+        assert _close(g["optF"][ok], o["optF"][ok]) and _close(g["x"][ok], o["x"][ok], 1e-8)
+    # bad arguments come back as codes, never as exceptions across the C boundary
+    assert L.gm_simplex(c.ctypes.data_as(C.c_void_p), wide.ctypes.data_as(C.c_void_p), 3, b.ctypes.data_as(C.c_void_p),
+                        7, 15, 0.0, None, C.byref(optF), x.ctypes.data_as(C.c_void_p), None, None) == S.GM_ERR_BAD_SHAPE
+    assert L.gm_free_root(123456) == S.GM_ERR_BAD_HANDLE
