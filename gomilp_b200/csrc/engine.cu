@@ -75,15 +75,16 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     P.max_pivots = g.opt.max_pivots;
     P.refactor_period = g.opt.refactor_period;
     const gm::WsLayout wr = gm::ws_layout(m, n, kSmemThreads, true);
-    const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads);
+    const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads, false, false, true);   // tier 2
+    const gm::WsLayout w3 = gm::ws_layout(m, n, kHbmThreads, false, true, true);    // tier 3
     const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads, false, true);
     const size_t smem_reg = wr.big_bytes + wr.small_bytes;
     const size_t smem_all = w1.big_bytes + w1.small_bytes;
     const bool fits_reg = m <= 64 && smem_reg + 64 <= g.smem_optin;
     const bool fits_smem = smem_all + 64 <= g.smem_optin;
     const bool fits_small = w2.small_bytes + 64 <= g.smem_optin;
-    const size_t bi_bytes = (w2.big_doubles - w2.Bi) * sizeof(double);
-    const bool fits_bismem = bi_bytes + w2.small_bytes + 64 <= g.smem_optin;
+    const size_t bi_bytes = (w3.big_doubles - w3.Bi) * sizeof(double);
+    const bool fits_bismem = bi_bytes + w3.small_bytes + 64 <= g.smem_optin;
     int tier = g.opt.force_tier;
     if (tier == 0) tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_bismem ? 3 : (fits_small ? 4 : 5)));
     if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_bismem) ||
@@ -113,13 +114,13 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         block = kHbmThreads;
         P.hbm_layout = 1;
         // per-CTA HBM slice: W only (tier 3), W + Bi (tier 4), everything (tier 5)
-        const size_t per_cta = tier == 3 ? w2.Bi : (tier == 4 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8));
+        const size_t per_cta = tier == 3 ? w3.Bi : (tier == 4 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8));
         grid = (int)std::min<long long>(P.count, (long long)g.sms);
         CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));
         P.work = work;
         P.work_stride = (long long)per_cta;
         if (tier == 3) {
-            smem = bi_bytes + w2.small_bytes;
+            smem = bi_bytes + w3.small_bytes;
         } else if (tier == 4) {
             // TMA staging ring: up to 3 stages of 32 KB if they fit beside the vectors
             const size_t stage = 32768;

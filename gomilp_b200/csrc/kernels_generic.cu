@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(gm_kernels::kHbmThreads, 1) simplex_wave_gener
     __shared__ unsigned long long bars[8];
     const int T = (int)blockDim.x;
     const bool hbm = P.hbm_layout != 0;
-    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, hbm);
+    const gm::WsLayout w = gm::ws_layout(P.m0 + P.L, P.n0 + P.L, T, false, hbm, P.tier == 2 || P.tier == 3);
     double* work = P.work ? P.work + (size_t)blockIdx.x * P.work_stride : nullptr;
     // one call site: the solver is large and fully inlined
     double *wbase, *bibase, *small, *ring = nullptr;

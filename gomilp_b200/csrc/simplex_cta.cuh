@@ -99,7 +99,7 @@ struct WsLayout {
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline WsLayout ws_layout(int m, int n, int T, bool reg = false, bool hbm = false) {
+inline WsLayout ws_layout(int m, int n, int T, bool reg = false, bool hbm = false, bool bi_smem = false) {
     WsLayout w;
     if (reg) {
         int ld = n + 1;
@@ -111,6 +111,11 @@ inline WsLayout ws_layout(int m, int n, int T, bool reg = false, bool hbm = fals
     } else {
         w.ldw = hbm ? ((n + 2 + 3) & ~3) : ((n + 1) | 1);
         w.ldb = hbm ? ((m + 3) & ~3) : (m | 1);
+        if (bi_smem) {  // quad-mapped loop: 8 rows x 4 consecutive columns per warp access -> stride = 4 (mod 16)
+            int ld = m;
+            while ((ld & 15) != 4) ++ld;
+            w.ldb = ld;
+        }
         w.wrows = m;
         w.vlen = m;
     }
@@ -177,6 +182,7 @@ struct SolverT {
     unsigned long long* ring_bar;
     int ring_stage_doubles, ring_ns, ring_uses, stream_min_m;
     int* sel;  // row list of the current stream (aliases inb: the flags are dead inside the main loop)
+    bool bi_smem;    // tiers 2, 3: Bi lives in shared memory with a quad-friendly row stride
     bool w_loaded;   // REG tier: W holds [A | art] in ORIGINAL column order for the current LP
     // counters (uniform across the CTA)
     int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
@@ -1040,6 +1046,7 @@ struct SolverT {
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
         if constexpr (REG) return main_loop_reg(tol, phase, fresh);
+        if (bi_smem && gm_nthreads() <= 1024) return main_loop_quad(tol, phase, fresh);
         if (ring != nullptr && m >= stream_min_m && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
             ((m + 1) & ~1) <= ring_stage_doubles)
             return main_loop_stream(tol, phase, fresh);
@@ -1541,6 +1548,151 @@ struct SolverT {
         return true;
     }
 
+    // Tiers 2-3 main loop: the register tier's schedule with the basis inverse read from shared memory.
+    // Thread (r = t>>2, q = t&3) owns columns j = q (mod 4) of row i0 + r for every block of T/4 rows; quads reduce
+    // by shuffles, first-minima by REDUX. Four barriers per pivot plus one to stage the entering column.
+    GM_DEV int main_loop_quad(double tol, int phase, bool fresh) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int rq = t >> 2, q = t & 3, lane = t & 31, warp = t >> 5, nw = T >> 5, RB = T >> 2;
+        int since = 0;
+        auto cross = [&](const double* rv, const int* ri, double& v, int& i) {
+            v = lane < nw ? rv[lane] : INFINITY;
+            i = lane < nw ? ri[lane] : INT_MAX;
+            warp_argmin(v, i);
+        };
+        for (;;) {
+            if (piv1 + piv2 >= max_pivots) return GM_ERR_ITERATION_LIMIT;
+            // ---- pricing: r = cn - an^T y (:236-250)
+            double bestv = INFINITY;
+            int besti = INT_MAX;
+            for (int k0 = 0; k0 < nn; k0 += RB) {
+                if (k0 + 8 * warp >= nn) break;  // warp-uniform
+                const int k = k0 + rq;
+                const bool valid = k < nn;
+                const double* wc = W + m + (valid ? k : 0);
+                double a0 = 0, a1 = 0;
+                int i = q;
+                for (; i + 4 < m; i += 8) {
+                    a0 += y[i] * wc[(size_t)i * ldw];
+                    a1 += y[i + 4] * wc[(size_t)(i + 4) * ldw];
+                }
+                if (i < m) a0 += y[i] * wc[(size_t)i * ldw];
+                double acc = a0 + a1;
+                acc += gm_shfl_xor(acc, 1);
+                acc += gm_shfl_xor(acc, 2);
+                if (valid) {
+                    const double rk = cn[k] - acc;
+                    if (q == 0) r[k] = fabs(rk) < GM_R_ROUND_TOL ? 0.0 : rk;
+                    if (rk == rk && (besti == INT_MAX || rk < bestv)) { bestv = rk; besti = k; }
+                }
+            }
+            if (besti == INT_MAX) bestv = INFINITY;
+            warp_argmin(bestv, besti);
+            if (lane == 0) { red[warp] = bestv; redi[warp] = besti; }
+            gm_sync();  // (1)
+            cross(red, redi, bestv, besti);
+            if (besti == INT_MAX || bestv >= -tol || (!fresh && bestv > -1e-9 * cscale)) {
+                gm_sync();
+                if (!fresh) {
+                    const int rc = polish();
+                    if (rc != GM_OK) return rc;
+                    fresh = true;
+                    continue;
+                }
+                return GM_OK;
+            }
+            int e = besti;
+            double re = bestv;
+            // ---- entering column staged once, then FTRAN + ratio test (:306-342, :268)
+            for (int i = t; i < m; i += T) t1[i] = W[(size_t)i * ldw + m + e];
+            gm_sync();  // (2)
+            double mvv = INFINITY;
+            int mi = INT_MAX;
+            for (int i0 = 0; i0 < m; i0 += RB) {
+                if (i0 + 8 * warp >= m) break;  // warp-uniform
+                const int i = i0 + rq;
+                const bool valid = i < m;
+                const double* brow = Bi + (size_t)(valid ? i : 0) * ldb;
+                double a0 = 0, a1 = 0;
+                int j = q;
+                for (; j + 4 < m; j += 8) {
+                    a0 += brow[j] * t1[j];
+                    a1 += brow[j + 4] * t1[j + 4];
+                }
+                if (j < m) a0 += brow[j] * t1[j];
+                double alpha = a0 + a1;
+                alpha += gm_shfl_xor(alpha, 1);
+                alpha += gm_shfl_xor(alpha, 2);
+                if (valid) {
+                    double d = -alpha;
+                    if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+                    double mvi = d < 0.0 ? xb[i] / fabs(d) : INFINITY;
+                    if (q == 0) { al[i] = alpha; mv[i] = mvi; }
+                    if (mvi == mvi && (mi == INT_MAX || mvi < mvv)) { mvv = mvi; mi = i; }
+                }
+            }
+            if (mi == INT_MAX) mvv = INFINITY;
+            warp_argmin(mvv, mi);
+            if (lane == 0) { red[32 + warp] = mvv; redi[32 + warp] = mi; }
+            gm_sync();  // (3)
+            cross(red + 32, redi + 32, mvv, mi);
+            if (mi == INT_MAX) mi = 0;
+            if (mvv == INFINITY) { gm_sync(); return GM_ERR_UNBOUNDED; }
+            int l = mi;
+            if (mvv <= 0.0) {  // :268-277
+                nbland++;
+                gm_sync();
+                const int rc = replace_bland(l, e);
+                if (rc != GM_OK) return rc;
+                re = r[e];
+            }
+            // ---- basis change (:280-292)
+            const double ap = al[l];
+            const double inv = 1.0 / ap;
+            const double theta = xb[l] * inv;
+            for (int j = t; j < m; j += T) prow[j] = Bi[(size_t)l * ldb + j] * inv;
+            gm_sync();  // (4)
+            for (int i0 = 0; i0 < m; i0 += RB) {
+                if (i0 + 8 * warp >= m) break;
+                const int i = i0 + rq;
+                if (i < m) {
+                    double* brow = Bi + (size_t)i * ldb;
+                    if (i == l) {
+                        for (int j = q; j < m; j += 4) brow[j] = prow[j];
+                    } else {
+                        const double f = al[i];
+                        if (f != 0.0)
+                            for (int j = q; j < m; j += 4) brow[j] -= f * prow[j];
+                    }
+                }
+            }
+            for (int i = t; i < m; i += T) {
+                xb[i] = (i == l) ? theta : xb[i] - al[i] * theta;
+                y[i] += re * prow[i];
+                const double a = W[(size_t)i * ldw + l];
+                W[(size_t)i * ldw + l] = W[(size_t)i * ldw + m + e];
+                W[(size_t)i * ldw + m + e] = a;
+            }
+            if (t == 0) {
+                const int v = basic[l];
+                basic[l] = nonbasic[e];
+                nonbasic[e] = v;
+                const double cc = cb[l];
+                cb[l] = cn[e];
+                cn[e] = cc;
+            }
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            gm_sync();  // (5)
+            if (++since >= refactor_period) {
+                const int rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+            }
+        }
+    }
+
     // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
     GM_DEV int find_initial_basic(bool& fresh, bool warm) {
         const int t = gm_tid(), T = gm_nthreads();
@@ -1780,7 +1932,8 @@ struct SolverT {
         stream_min_m = P.stream_min_m;
         m0 = P.m0; n0 = P.n0; L = P.L; lda = P.lda;
         m = m0 + L; n = n0 + L;
-        const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0);
+        const WsLayout w = ws_layout(m, n, gm_nthreads(), REG, P.hbm_layout != 0, P.tier == 2 || P.tier == 3);
+        bi_smem = !REG && (P.tier == 2 || P.tier == 3);
         ldw = w.ldw; ldb = w.ldb; wrows = w.wrows; vlen = w.vlen;
         W = wbase; Bi = bibase;
         xb = small + w.xb; cb = small + w.cb; y = small + w.y; al = small + w.al;

@@ -6,7 +6,8 @@
 #include "cta_emu.hpp"
 #include "../../gomilp_b200/csrc/simplex_cta.cuh"
 
-static const int* g_emu_lp_list = nullptr;  // retry launches: work item k solves LP list[k]
+static const int* g_emu_lp_list = nullptr;
+static int g_emu_quad = 0;  // 1: run the generic solver as tier 2 (quad-mapped main loop)  // retry launches: work item k solves LP list[k]
 
 extern "C" {
 
@@ -58,7 +59,8 @@ int emu_simplex_batch_ex(int count, const double* c, const double* A, const doub
     P.hbm_layout = hbm ? 1 : 0;
     P.ring_stages = ring_stages;
     P.ring_stage_bytes = ring_stage_bytes;
-    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T, reg != 0, hbm);
+    P.tier = reg ? 1 : (g_emu_quad ? 2 : (hbm ? 4 : 5));
+    gm::WsLayout w = gm::ws_layout(m0 + L, n0 + L, T, reg != 0, hbm, P.tier == 2);
     std::vector<double> ringbuf((size_t)ring_stages * ring_stage_bytes / 8 + 32, 0.0);
     double* ring = hbm ? reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ringbuf.data()) + 127) & ~uintptr_t(127)) : nullptr;
     unsigned long long bars[8] = {0};
@@ -99,6 +101,7 @@ int g_reg = 0;
 
 extern "C" {
 void emu_set_threads(int T, int reg) { g_T = T; g_reg = reg; }
+void emu_set_quad(int on) { g_emu_quad = on; }
 int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
                    gm_root_t* out) {
     EmuRoot r;

@@ -45,7 +45,7 @@ def _p(a):
 
 
 def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_basic=None, T=64,
-                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False, reg=False, ring_stages=0, ring_stage_bytes=4096):
+                  max_pivots=0, refactor_period=0, shared_root=False, x_len=None, shuffle_order=False, reg=False, ring_stages=0, ring_stage_bytes=4096, quad=False):
     """Batch of LPs through the emulated kernel.
 
     Plain batch: A [count,m,n], c [count,n], b [count,m]. Wave mode (shared_root=True): one root
@@ -75,6 +75,7 @@ def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_ba
     basis = np.zeros((count, m), dtype=np.int64)
     stats = np.zeros((count, 8), dtype=np.int32)
     ib = None if initial_basic is None else np.ascontiguousarray(initial_basic, dtype=np.int64)
+    lib().emu_set_quad(C.c_int(int(quad)))
     rc = lib().emu_simplex_batch(C.c_int(count), _p(c), _p(A), _p(b), C.c_longlong(cs), C.c_longlong(As),
                                  C.c_longlong(bs), C.c_int(n0), C.c_int(m0), C.c_int(n0), C.c_int(L), _p(bvar),
                                  _p(bsign), _p(brhs), _p(ib), C.c_double(tol), C.c_int(max_pivots),
@@ -97,10 +98,11 @@ _WCB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double
 
 
 def milp_solve(c, A=None, b=None, G=None, h=None, integrality=None, heuristic=0, mode=0, node_limit=0,
-               time_limit_s=0.0, T=64, reg=False):
+               time_limit_s=0.0, T=64, reg=False, quad=False):
     """The product's gm_milp_solve (bnb_host.cpp) with every wave solved by the emulated kernel."""
     L = lib()
     L.emu_set_threads(C.c_int(256 if reg else T), C.c_int(int(reg)))
+    L.emu_set_quad(C.c_int(int(quad)))
     c = np.ascontiguousarray(c, dtype=np.float64)
     nvar = c.shape[0]
     meq = 0 if A is None else np.asarray(A).shape[0]

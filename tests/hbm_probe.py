@@ -25,7 +25,7 @@ def slack_form(rng, m, n, count):
 
 def main():
     gm.init(0)
-    for (m, n, count, cap) in [(100, 200, 296, 100), (150, 300, 296, 150), (256, 512, 296, 200), (512, 1024, 148, 200),
+    for (m, n, count, cap) in [(70, 140, 592, 100), (100, 200, 296, 100), (150, 300, 296, 150), (256, 512, 296, 200), (512, 1024, 148, 200),
                                (700, 1200, 148, 150), (1024, 2048, 148, 100)]:
         rng = np.random.default_rng(42)
         base = min(count, 8)

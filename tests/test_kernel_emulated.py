@@ -31,6 +31,20 @@ def test_emulated_kernel_matches_oracle_on_feasible_lps(T, reg):
         assert np.max(np.abs(np.einsum("kij,kj->ki", A, g["x"]) - b)) < 1e-9
 
 
+def test_emulated_quad_mapped_tier_matches_oracle():
+    """Tiers 2-3 main loop (basis inverse in shared memory, quad per row, REDUX first-minima)."""
+    rng = np.random.default_rng(78)
+    for (m, n, k, T) in [(3, 7, 6, 64), (17, 40, 4, 64), (70, 140, 1, 128)]:
+        c, A, b = feasible_bounded_lp(rng, m, n, k)
+        g = E.simplex_batch(c, A, b, T=T, quad=True, shuffle_order=True)
+        o = oracle.simplex_batch(c, A, b)
+        assert (g["status"] == o["status"]).all() and _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
+    c, A, b = raw_lp(rng, 6, 11, 24, 0.3)
+    g = E.simplex_batch(c, A, b, T=64, quad=True)
+    o = oracle.simplex_batch(c, A, b, max_pivots=5000)
+    assert (g["status"] == o["status"]).sum() >= 23
+
+
 def test_emulated_tma_streaming_tier_matches_oracle():
     """The HBM tier's main loop (TMA bulk-copy ring emulated as memcpy + byte-counting mbarrier)."""
     rng = np.random.default_rng(77)
