@@ -873,33 +873,42 @@ struct SolverT {
     // ---- the last m columns taken as a permutation matrix (pure slack basis): Bi = B^T ---------------
     GM_DEV bool try_permutation_basis() {
         const int t = gm_tid(), T = gm_nthreads();
-        for (int i = t; i < m; i += T) ipiv[i] = -1;
+        // quick reject on the very last column (dense problems leave here after one round trip)
+        if (n - 1 < n0) {
+            const double cnt0 = block_sum(m, [&](int i) { return src_a(i, n - 1) != 0.0 ? 1.0 : 0.0; });
+            if (cnt0 != 1.0) return false;
+        }
+        // Non-zeros of the last m columns are counted with one coalesced, fully parallel sweep (inb[p] = count,
+        // +1000 for an entry that is not 1; basic[p] = a row holding one), not column by column.
+        for (int i = t; i < m; i += T) { ipiv[i] = -1; inb[i] = 0; basic[i] = -1; }
         gm_sync();
-        int ok = 1;
+        const int nstruct = n0 - (n - m) > 0 ? n0 - (n - m) : 0;  // how many of the m columns are root columns (v < n0)
+        // slack columns of branch rows: a single 1 at row m0 + (v - n0) (convertToEqualities)
         for (int p = t; p < m; p += T) {
             const int v = n - 1 - p;
-            int row = -1, cnt = 0;
-            if (v >= n0) {  // slack of branch row v-n0: a single 1 (convertToEqualities)
-                row = m0 + (v - n0);
-                cnt = 1;
-            } else {
-                for (int i = 0; i < m; ++i) {
-                    const double a = src_a(i, v);
-                    if (a != 0.0) {
-                        ++cnt;
-                        row = i;
-                        if (a != 1.0) cnt = 99;
-                        if (cnt > 1) break;
-                    }
+            if (v >= n0) { inb[p] = 1; basic[p] = m0 + (v - n0); }
+        }
+        gm_sync();
+        if (nstruct > 0) {
+            const int p0 = m - nstruct;  // positions p0..m-1 hold columns v = n-1-p < n0
+            for_each_2d(m, nstruct, [&](int i, int pp) {
+                const int p = p0 + pp;
+                const double a = src_a(i, n - 1 - p);
+                if (a != 0.0) {
+                    gm_atomic_add(&inb[p], a == 1.0 ? 1 : 1000);
+                    basic[p] = i;
                 }
-            }
-            if (cnt != 1) { ok = 0; row = -1; }
-            else ipiv[row] = p;  // two columns on one row are caught below
-            inb[p] = row;
+            });
+            gm_sync();
+        }
+        int ok = 1;
+        for (int p = t; p < m; p += T) {
+            if (inb[p] != 1) ok = 0;
+            else ipiv[basic[p]] = p;  // two columns on one row are caught below
         }
         gm_sync();
         for (int p = t; p < m; p += T)
-            if (inb[p] < 0 || ipiv[inb[p]] != p) ok = 0;
+            if (ok && (basic[p] < 0 || ipiv[basic[p]] != p)) ok = 0;
         const int bad = block_min_int(T, [&](int k) { return (k == t && !ok) ? 0 : INT_MAX; });
         if (bad != INT_MAX) return false;
         for (int p = t; p < m; p += T) basic[p] = n - 1 - p;

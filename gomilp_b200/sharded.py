@@ -146,21 +146,31 @@ def milp_solve_sharded(c, A, b, G, h, integrality, *, solve_wave, group=None, de
         kms = 0.0
         if hi > lo:
             st, z, xs, piv, kms = solve_wave(c0, A0, b0, bvar[lo:hi], bsign[lo:hi], brhs[lo:hi])
-            for k in range(hi - lo):
-                feas, bv, fl = 0.0, -1.0, 0.0
-                if st[k] == S.GM_OK:
-                    if feasible_for_ip(integ, xs[k]):
-                        feas = 1.0
+            # per-node record, vectorised over the block: integer-feasible? else branch variable and floor
+            imask = integ.astype(bool)
+            okm = st == S.GM_OK
+            frac = (xs != np.trunc(xs)) & imask[None, :]
+            feas = okm & ~frac.any(axis=1)
+            need = okm & ~feas
+            bvv = np.full(hi - lo, -1.0)
+            flv = np.zeros(hi - lo)
+            if need.any():
+                if mode == S.GM_BNB_COMPAT:
+                    on = np.full(hi - lo, maxfun_point(c0, integ))
+                elif heuristic == S.GM_BRANCH_NAIVE:
+                    on = np.array([fixed_point(heuristic, c0, xs[k], integ, int(bvar[lo + k, -1]) if depth > 0 else -1)
+                                   if need[k] else 0 for k in range(hi - lo)])
+                else:
+                    if heuristic == S.GM_BRANCH_MOST_INFEASIBLE:
+                        f = xs - np.floor(xs)
+                        score = 0.5 - np.abs(0.5 - f)
                     else:
-                        if mode == S.GM_BNB_COMPAT:
-                            on = maxfun_point(c0, integ)
-                        else:
-                            last = int(bvar[lo + k, -1]) if depth > 0 else -1
-                            on = fixed_point(heuristic, c0, xs[k], integ, last)
-                            if on < 0:
-                                on = maxfun_point(c0, integ)
-                        bv, fl = float(on), float(np.floor(xs[k][on]))
-                rec[k] = (float(st[k]), z[k], feas, bv, fl, float(piv[k]))
+                        score = np.broadcast_to(np.abs(c0), xs.shape)
+                    on = np.argmax(np.where(frac, score, -1.0), axis=1)  # first maximum, like fixed_point()
+                idx = np.nonzero(need)[0]
+                bvv[idx] = on[idx]
+                flv[idx] = np.floor(xs[idx, on[idx].astype(np.int64)])
+            rec = np.stack([st.astype(np.float64), z, feas.astype(np.float64), bvv, flv, piv.astype(np.float64)], axis=1)
         # ---- the only exchange of the wave: one 48-byte record per node -------------------------------
         if world > 1:
             sizes = [fifo_block(count, world, r) for r in range(world)]
