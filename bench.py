@@ -152,14 +152,19 @@ def bnb_extra(gm):
         for warm_up_mode in (1, 1 | 4):  # also loads the warm-start kernel before anything is timed
             gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=warm_up_mode, heuristic=1,
                           node_limit=256, keep_log=False)
-        t0 = time.perf_counter()
-        r = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=1, heuristic=1, node_limit=8192,
-                          keep_log=False)
-        dt = time.perf_counter() - t0
-        t1 = time.perf_counter()
-        rw = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=1 | 4, heuristic=1,
-                           node_limit=8192, keep_log=False)
-        dtw = time.perf_counter() - t1
+        def best_of(mode, reps=3):
+            best = None
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                res = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=mode, heuristic=1,
+                                    node_limit=8192, keep_log=False)
+                el = time.perf_counter() - t0
+                if best is None or el < best[1]:
+                    best = (res, el)
+            return best
+
+        r, dt = best_of(1)       # wall clock of a host-driven loop of ~14 small launches: best of 3
+        rw, dtw = best_of(1 | 4)
         return {"nodes_per_sec": r.nodes / dt, "nodes": r.nodes, "waves": r.waves, "pivots": r.pivots,
                 "wall_s": dt, "device_ms": r.device_ms, "gpus": 1,
                 "warm_start": {"nodes_per_sec": rw.nodes / dtw, "nodes": rw.nodes, "pivots": rw.pivots,
