@@ -324,3 +324,24 @@ def test_edge_cases_empty_ragged_and_strided():
     assert L.gm_simplex(c.ctypes.data_as(C.c_void_p), wide.ctypes.data_as(C.c_void_p), 3, b.ctypes.data_as(C.c_void_p),
                         7, 15, 0.0, None, C.byref(optF), x.ctypes.data_as(C.c_void_p), None, None) == S.GM_ERR_BAD_SHAPE
     assert L.gm_free_root(123456) == S.GM_ERR_BAD_HANDLE
+
+
+def test_results_are_bitwise_reproducible_run_to_run():
+    """compute-sanitizer is closed on this GPU pool, so shared-memory races cannot be checked directly; a race would
+    show as run-to-run differences (the persistent CTAs pick LPs in a different order every launch)."""
+    rng = np.random.default_rng(99)
+    c, A, b = feasible_bounded_lp(rng, 48, 100, 600)
+    c2, A2, b2 = raw_lp(rng, 20, 45, 600, 0.1)
+    try:
+        for tier in (1, 2, 3, 4):
+            gm.set_options(force_tier=tier)
+            runs = [gm.simplex_batch(c, A, b) for _ in range(3)]
+            runs2 = [gm.simplex_batch(c2, A2, b2) for _ in range(2)]
+            for r in runs[1:]:
+                assert np.array_equal(r["status"], runs[0]["status"]) and np.array_equal(r["x"], runs[0]["x"])
+                assert np.array_equal(r["optF"], runs[0]["optF"]) and np.array_equal(r["basis"], runs[0]["basis"])
+                assert np.array_equal(r["pivots"], runs[0]["pivots"])
+            assert np.array_equal(runs2[1]["status"], runs2[0]["status"])
+            assert np.array_equal(runs2[1]["x"], runs2[0]["x"])
+    finally:
+        gm.set_options()
