@@ -560,9 +560,9 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const size_t need = (size_t)nodes * (size_t)m * (size_t)m * 8 + (size_t)nodes * (size_t)m * 8;
-    if (need < free_b / 2) {
-        CK(cudaMalloc(&cur_bi, (size_t)nodes * m * m * 8));
-        CK(cudaMalloc(&cur_basis, (size_t)nodes * m * 8));
+    if (need < free_b / 2) {  // stream-ordered pool: no device-wide synchronisation per wave
+        CK(cudaMallocAsync(&cur_bi, (size_t)nodes * m * m * 8, st));
+        CK(cudaMallocAsync(&cur_basis, (size_t)nodes * m * 8, st));
     }
     DevBuf dbv(st), dbs(st), dbr(st), dpar(st), dst(st), dF(st), dX(st), dB(st), dS(st), dlist(st);
     CK(cudaEventRecord(se.e[0], st));
@@ -621,9 +621,9 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
         if (basis) CK(cudaMemcpyAsync(basis, P.basis, sizeof(int64_t) * nodes * m, cudaMemcpyDeviceToHost, st));
         if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * nodes * 8, cudaMemcpyDeviceToHost, st));
     }
+    if (r->prev_bi) cudaFreeAsync(r->prev_bi, st);
+    if (r->prev_basis) cudaFreeAsync(r->prev_basis, st);
     cudaStreamSynchronize(st);
-    cudaFree(r->prev_bi);
-    cudaFree(r->prev_basis);
     r->prev_bi = cur_bi;
     r->prev_basis = cur_basis;
     r->prev_nodes = cur_bi ? nodes : 0;
