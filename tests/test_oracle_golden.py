@@ -87,3 +87,31 @@ def test_oracle_agrees_with_highs_on_random_lps():
         elif r.status == S.GM_ERR_UNBOUNDED:
             assert h.status in (3, 2) or h.status == 4
     assert checked == 60
+
+
+def test_oracle_linear_algebra_against_lapack():
+    """The restated Gonum/LAPACK pieces behind every SolveVec / mat.Cond (lu.go:63-84,293-325, matrix.go:284-322):
+    solutions agree with LAPACK (numpy), condition estimates bracket the exact 1-norm condition number from below
+    (Hager's estimator never overestimates) and flag singular systems the way LU.Solve does."""
+    rng = np.random.default_rng(2024)
+    for n in (1, 2, 5, 17, 64, 90):
+        a = rng.standard_normal((n, n))
+        b = rng.standard_normal(n)
+        for tr in (False, True):
+            rc, x, cond = oracle.solve_vec(a, b, transpose=tr)
+            want = np.linalg.solve(a.T if tr else a, b)
+            assert rc == 0 and np.allclose(x, want, rtol=1e-9, atol=1e-11)
+        exact = np.linalg.cond(a, 1)
+        est = oracle.cond1(a)
+        assert 0.1 * exact <= est <= exact * (1 + 1e-9)
+        # tall slices, as findLinearlyIndependent sees them: cond_1 of the R factor
+        if n >= 5:
+            k = n // 2
+            r = np.linalg.qr(a[:, :k], mode="r")
+            exact_r = np.linalg.cond(r, 1)
+            est_r = oracle.cond1(a[:, :k])
+            assert 0.1 * exact_r <= est_r <= exact_r * (1 + 1e-9)
+    sing = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [1.0, 0.0, 1.0]])
+    rc, _, _ = oracle.solve_vec(sing, np.ones(3))
+    assert rc != 0
+    assert oracle.cond1(sing) > 1e15
