@@ -8,8 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libgomilp_b200.so")
-SOURCES = ["engine.cu", "kernels_reg.cu", "kernels_generic.cu", "bnb_host.cpp"]
-HEADERS = ["simplex_cta.cuh", "cta_rt.cuh", "kernels.h", os.path.join("..", "..", "include", "gomilp_b200.h"),
+SOURCES = ["engine.cu", "kernels_reg.cu", "kernels_generic.cu", "kernels_coop.cu", "bnb_device.cu", "bnb_host.cpp"]
+HEADERS = ["simplex_cta.cuh", "cta_rt.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "gomilp_b200.h"),
            os.path.join("..", "..", "include", "gomilp_status.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -17,8 +17,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 INC = os.path.join("..", "..", "include")
 DEPS = {
-    "engine.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_b200.h"),
+    "engine.cu": ["engine.h", "kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_b200.h"),
                   os.path.join(INC, "gomilp_status.h")],
+    "bnb_device.cu": ["engine.h", "kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_b200.h"),
+                      os.path.join(INC, "gomilp_status.h")],
+    "kernels_coop.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
     "kernels_reg.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
     "kernels_generic.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
     "bnb_host.cpp": [os.path.join(INC, "gomilp_b200.h"), os.path.join(INC, "gomilp_status.h")],
@@ -63,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         logs.append(" ".join(cmd) + "\n" + out)
         ok = ok and pr.returncode == 0
     if ok:
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-ldl"]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         logs.append(" ".join(cmd) + "\n" + res.stdout)
         ok = res.returncode == 0

@@ -35,7 +35,7 @@ class gm_timing(C.Structure):
 
 class gm_options(C.Structure):
     _fields_ = [("max_pivots", C.c_int32), ("refactor_period", C.c_int32), ("force_tier", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("coop_group", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class gm_milp_result(C.Structure):
@@ -49,7 +49,8 @@ WAVE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_dou
 
 EXPORTS = ["gm_device_count", "gm_init", "gm_shutdown", "gm_last_error", "gm_last_timing", "gm_set_options",
            "gm_simplex", "gm_simplex_batch", "gm_simplex_batch_device", "gm_upload_root", "gm_free_root",
-           "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve"]
+           "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve", "gm_trace_arm", "gm_trace_fetch",
+           "gm_milp_solve_device", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
 
 
 def lib():
@@ -76,9 +77,15 @@ def lib():
     L.gm_solve_wave_warm.argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.gm_milp_solve.argtypes = [i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, i32, i64, f64, vp,
                                 C.POINTER(gm_milp_result), DECISION_CB, WAVE_CB, vp]
+    L.gm_milp_solve_device.argtypes = L.gm_milp_solve.argtypes
+    L.gm_comm_unique_id.argtypes = [vp]
+    L.gm_comm_init.argtypes = [i32, i32, vp]
+    L.gm_trace_arm.argtypes = [i64, i64]
+    L.gm_trace_fetch.argtypes = [vp, i64]
     for name in EXPORTS:
         if name != "gm_last_error":
             getattr(L, name).restype = C.c_int
+    L.gm_trace_fetch.restype = C.c_int64
     _lib = L
     return L
 
@@ -104,9 +111,23 @@ def init(device: int = 0):
     _check(lib().gm_init(device))
 
 
-def set_options(max_pivots: int = 0, refactor_period: int = 0, force_tier: int = 0, no_tma_ring: bool = False):
-    o = gm_options(max_pivots, refactor_period, force_tier, 1 if no_tma_ring else 0)
+def set_options(max_pivots: int = 0, refactor_period: int = 0, force_tier: int = 0, no_tma_ring: bool = False,
+                coop_group: int = 0):
+    o = gm_options(max_pivots, refactor_period, force_tier, 1 if no_tma_ring else 0, coop_group, 0)
     _check(lib().gm_set_options(C.byref(o)))
+
+
+def trace_arm(lp_index: int = 0, cap: int = 256):
+    """The next host-buffer compute call on this thread records the first `cap` pivots of LP `lp_index`."""
+    _check(lib().gm_trace_arm(lp_index, cap))
+
+
+def trace_fetch(cap: int = 256) -> np.ndarray:
+    """Rows (phase, entering variable, leaving variable, bland) of the armed call; unused rows trimmed."""
+    rows = np.full((cap, 4), -1, dtype=np.int32)
+    k = lib().gm_trace_fetch(_p(rows), cap)
+    rows = rows[:k]
+    return rows[rows[:, 0] >= 0]
 
 
 def last_timing() -> dict:
@@ -269,3 +290,20 @@ def milp_solve(c, A=None, b=None, G=None, h=None, integrality=None, heuristic: i
     xl = int(res.x_len)
     return MilpResult(res.status, res.lp_status, x[:xl].copy() if xl else None, res.z, res.nodes, res.waves,
                       res.pivots, res.device_ms, log, wlog)
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id created by rank 0; hand it to the other ranks (torch.distributed, a file, a channel)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().gm_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank: int, world: int, uid: bytes):
+    """Joins the calling thread (bound to its device by init()) to the communicator of `world` ranks."""
+    assert len(uid) == 128
+    _check(lib().gm_comm_init(rank, world, C.create_string_buffer(uid, 128)))
+
+
+def comm_destroy():
+    lib().gm_comm_destroy()

@@ -87,6 +87,9 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
                              int64_t nineq, const double* G, const double* h, const uint8_t* integrality,
                              int32_t heuristic, int32_t mode, int64_t node_limit, double time_limit_s, double* x_out,
                              gm_milp_result* result, gm_decision_cb on_decision, gm_wave_cb on_wave, void* user) {
+    if (mode & GM_BNB_DEVICE_SCAN)  // decisions on the device, sharded when a communicator is set (bnb_device.cu)
+        return gm_milp_solve_device(nvar, c, meq, A, b, nineq, G, h, integrality, heuristic, mode & ~GM_BNB_DEVICE_SCAN,
+                                    node_limit, time_limit_s, x_out, result, on_decision, on_wave, user);
     if (!result || !x_out || !c || !integrality || nvar <= 0 || meq < 0 || nineq < 0) return GM_ERR_BAD_ARGUMENT;
     if ((meq > 0 && (!A || !b)) || (nineq > 0 && (!G || !h)) || meq + nineq == 0) return GM_ERR_BAD_ARGUMENT;
     const auto t0 = std::chrono::steady_clock::now();

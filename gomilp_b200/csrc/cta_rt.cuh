@@ -33,6 +33,24 @@ GM_DEV int gm_any(int pred) { return __any_sync(0xffffffffu, pred); }
 GM_DEV int gm_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 GM_DEV double gm_ldg(const double* p) { return __ldg(p); }
 
+// ---- multi-CTA groups (the cooperative kernel: several CTAs of one cooperative launch work on one LP) ----------
+GM_DEV int gm_block_id() { return (int)blockIdx.x; }
+GM_DEV void gm_threadfence() { __threadfence(); }
+GM_DEV void gm_spin_pause() {}
+GM_DEV void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+GM_DEV unsigned long long gm_ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// One FP64 tensor-core step (SASS DMMA): D(8x8) = A(8x4) * B(4x8) + C, warp-wide. Lane l holds A[l>>2][l&3],
+// B[l&3][l>>2] and C/D[l>>2][2*(l&3) + {0,1}].
+GM_DEV void gm_dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on a shared-memory mbarrier -------------------
 GM_DEV unsigned gm_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 GM_DEV void gm_mbar_init(unsigned long long* bar, int count) {

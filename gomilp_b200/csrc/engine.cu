@@ -1,99 +1,189 @@
 // engine.cu — C ABI of libgomilp_b200.so (include/gomilp_b200.h): device management, host<->device
-// staging, tier selection and launch of the simplex wave kernel. No CPU fallback anywhere: every
+// staging, tier selection and launch of the simplex wave kernels. No CPU fallback anywhere: every
 // compute entry point returns GM_ERR_NO_DEVICE when no CUDA device is usable.
-#include <cuda_runtime.h>
+//
+// Threading / devices (SURVEY.md 8b "Threading"): the engine keeps one context PER DEVICE. A host thread is bound
+// to the device of its last gm_init(device) call (thread-local); threads that never called gm_init use the first
+// device any thread initialised. Roots remember their device, so a wave always runs where its root lives. Every
+// call takes its stream and events from a per-device pool; nothing global is written on the launch path except
+// under the engine mutex (options snapshot, root table).
+#include "engine.h"
 
-#include <atomic>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
-#include <map>
-#include <mutex>
-#include <string>
-#include <vector>
 
-#include "../../include/gomilp_b200.h"
-#include "kernels.h"
+namespace gm_engine {
 
-namespace {
-
-using gm_kernels::kHbmThreads;
-using gm_kernels::kSmemThreads;
-
-struct Root {
-    double *c = nullptr, *A = nullptr, *b = nullptr;
-    int m0 = 0, n0 = 0;
-    // warm-start state: final bases / inverses of the previous wave, kept in HBM for the children
-    double* prev_bi = nullptr;
-    long long* prev_basis = nullptr;
-    int64_t prev_nodes = 0;
-    int prev_m = 0;
-};
-
-struct Engine {
-    std::mutex mu;
-    bool ready = false;
-    int device = -1;
-    int sms = 0;
-    size_t smem_optin = 0;
-    gm_options opt{0, 0, 0, 0};
-    std::map<gm_root_t, Root> roots;
-    gm_root_t next_root = 1;
-};
 Engine g;
-
+thread_local int t_device = -1;
 thread_local std::string t_err;
 thread_local gm_timing t_timing{};
+thread_local TraceReq t_trace;
 
 int fail(cudaError_t e, const char* what) {
     t_err = std::string(what) + ": " + cudaGetErrorString(e);
     return GM_ERR_CUDA;
 }
-#define CK(call)                                   \
-    do {                                           \
-        cudaError_t e_ = (call);                   \
-        if (e_ != cudaSuccess) return fail(e_, #call); \
-    } while (0)
 
-int ensure_ready() {
-    if (g.ready) {
-        cudaSetDevice(g.device);  // bind the calling (possibly new) host thread
-        return GM_OK;
-    }
-    return gm_init(0);
+cudaError_t StreamEvents::init() {
+    cudaError_t r = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && r == cudaSuccess; ++i) r = cudaEventCreate(&e[i]);
+    return r;
+}
+StreamEvents::~StreamEvents() {
+    for (auto& ev : e)
+        if (ev) cudaEventDestroy(ev);
+    if (s) cudaStreamDestroy(s);
 }
 
-}  // namespace
+// A stream + 6 events for the duration of one call, recycled through the device's pool.
+StreamLease::StreamLease(DeviceCtx* d) : dev(d) {
+    {
+        std::lock_guard<std::mutex> lk(dev->mu);
+        if (!dev->pool.empty()) {
+            se = dev->pool.back();
+            dev->pool.pop_back();
+        }
+    }
+    if (!se) {
+        se = new StreamEvents();
+        err = se->init();
+    }
+}
+StreamLease::~StreamLease() {
+    if (!se) return;
+    if (err != cudaSuccess) { delete se; return; }
+    std::lock_guard<std::mutex> lk(dev->mu);
+    dev->pool.push_back(se);
+}
 
-namespace gm_internal {
+static int init_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        t_err = "no CUDA device (the engine has no CPU fallback)";
+        return GM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n || device >= kMaxDevices) return GM_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lk(g.mu);
+    DeviceCtx& d = g.dev[device];
+    CK(cudaSetDevice(device));
+    if (!d.ready) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        d.id = device;
+        d.sms = prop.multiProcessorCount;
+        d.smem_optin = prop.sharedMemPerBlockOptin;
+        d.coop_ok = prop.cooperativeLaunch != 0;
+        // dynamic shared-memory limits are a per-device function attribute: raised once here, never per launch
+        CK(gm_kernels::reg_set_smem_limit(d.smem_optin));
+        CK(gm_kernels::generic_set_smem_limit(d.smem_optin));
+        CK(gm_kernels::coop_prepare(d.smem_optin));
+        CK(gm_bnb_kernels_prepare());
+        // keep stream-ordered allocations cached across calls (the default pool trims at every synchronize)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        d.ready = true;
+    }
+    if (g.default_device < 0) g.default_device = device;
+    return GM_OK;
+}
+
+// Binds the calling thread to its device (see the header comment) and returns that device's context.
+int current_device(DeviceCtx** out) {
+    int dev = t_device;
+    if (dev < 0) {
+        std::lock_guard<std::mutex> lk(g.mu);
+        dev = g.default_device;
+    }
+    if (dev < 0) dev = 0;
+    if (!g.dev[dev].ready) {
+        const int rc = init_device(dev);
+        if (rc != GM_OK) return rc;
+    }
+    CK(cudaSetDevice(dev));
+    *out = &g.dev[dev];
+    return GM_OK;
+}
+
+int device_of_root(gm_root_t h, Root* out, DeviceCtx** dev) {
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        auto it = g.roots.find(h);
+        if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
+        *out = it->second;
+    }
+    CK(cudaSetDevice(out->device));
+    *dev = &g.dev[out->device];
+    return GM_OK;
+}
 
 // Launches the wave kernel over `P.count` LPs whose problem/outputs are already device-resident.
 // Fills work/queue fields of P. Asynchronous on `stream`; kernel time is recorded into ev0/ev1 if given.
-int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, gm_timing* tm) {
+int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, gm_timing* tm) {
+    using gm_kernels::kHbmThreads;
+    using gm_kernels::kSmemThreads;
     const int m = P.m0 + P.L, n = P.n0 + P.L;
     if (P.count <= 0) return GM_OK;
     if (m <= 0 || n <= 0) return GM_ERR_BAD_SHAPE;
-    P.max_pivots = g.opt.max_pivots;
-    P.refactor_period = g.opt.refactor_period;
+    gm_options opt;
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        opt = g.opt;
+    }
+    P.max_pivots = opt.max_pivots;
+    P.refactor_period = opt.refactor_period;
     const gm::WsLayout wr = gm::ws_layout(m, n, kSmemThreads, true);
     const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads, false, false, true);   // tier 2
     const gm::WsLayout w3 = gm::ws_layout(m, n, kHbmThreads, false, true, true);    // tier 3
     const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads, false, true);
     const size_t smem_reg = wr.big_bytes + wr.small_bytes;
     const size_t smem_all = w1.big_bytes + w1.small_bytes;
-    const bool fits_reg = m <= 64 && smem_reg + 64 <= g.smem_optin;
-    const bool fits_smem = smem_all + 64 <= g.smem_optin;
-    const bool fits_small = w2.small_bytes + 64 <= g.smem_optin;
+    const bool fits_reg = m <= 64 && smem_reg + 64 <= d.smem_optin;
+    const bool fits_smem = smem_all + 64 <= d.smem_optin;
+    const bool fits_small = w2.small_bytes + 64 <= d.smem_optin;
     const size_t bi_bytes = (w3.big_doubles - w3.Bi) * sizeof(double);
-    const bool fits_bismem = bi_bytes + w3.small_bytes + 64 <= g.smem_optin;
-    int tier = g.opt.force_tier;
-    if (tier == 0) tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_bismem ? 3 : (fits_small ? 4 : 5)));
+    const bool fits_bismem = bi_bytes + w3.small_bytes + 64 <= d.smem_optin;
+    // tier 6 (cooperative): fewer LPs than SMs and an LP big enough that one CTA per LP would crawl
+    int G = 0;
+    if (d.coop_ok && m < n) {
+        G = opt.coop_group > 0 ? opt.coop_group : d.sms / P.count;
+        G = std::min(G, std::max(1, m / 2));
+        G = std::min(G, d.sms);
+        if ((long long)G * P.count > d.sms) G = d.sms / P.count;
+    }
+    const gm::CoopLayout cl = gm::coop_layout(m, n, kHbmThreads, G > 0 ? G : 1);
+    const bool fits_coop = G >= 1 && cl.smem_bytes + 256 <= d.smem_optin;
+    int tier = opt.force_tier;
+    if (tier == 0) {
+        tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_bismem ? 3 : (fits_small ? 4 : 5)));
+        if (tier >= 2 && fits_coop && G >= 2 && m >= 96) tier = 6;
+    }
     if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_bismem) ||
-        (tier == 4 && !fits_small) || tier < 1 || tier > 5)
+        (tier == 4 && !fits_small) || (tier == 6 && !fits_coop) || tier < 1 || tier > 6)
         return GM_ERR_TOO_LARGE;
 
+    // pivot trace requested for this call (gm_trace_arm)
+    int* d_trace = nullptr;
+    if (t_trace.armed && !t_trace.in_flight) {
+        CK(cudaMallocAsync(&d_trace, sizeof(int) * 4 * (size_t)t_trace.cap, stream));
+        CK(cudaMemsetAsync(d_trace, 0xff, sizeof(int) * 4 * (size_t)t_trace.cap, stream));
+        P.trace = d_trace;
+        P.trace_cap = (int)t_trace.cap;
+        P.trace_lp = (int)t_trace.lp;
+        t_trace.in_flight = true;
+        t_trace.d_buf = d_trace;
+        t_trace.stream = stream;
+    }
+
     int* queue = nullptr;
-    CK(cudaMallocAsync(&queue, sizeof(int), stream));
-    CK(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+    const size_t qbytes = 16 + 8 * (size_t)std::max(1, P.count);  // queue counter, then one barrier counter per group
+    CK(cudaMallocAsync(&queue, qbytes, stream));
+    CK(cudaMemsetAsync(queue, 0, qbytes, stream));
     P.queue = queue;
     double* work = nullptr;
     int grid = 0, block = 0;
@@ -106,16 +196,33 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         if (tier == 1) CK(gm_kernels::reg_prepare(smem, &per_sm));
         else CK(gm_kernels::generic_prepare(block, smem, &per_sm));
         if (per_sm < 1) per_sm = 1;
-        grid = (int)std::min<long long>(P.count, (long long)g.sms * per_sm);
+        grid = (int)std::min<long long>(P.count, (long long)d.sms * per_sm);
         if (ev0) CK(cudaEventRecord(ev0, stream));
         if (tier == 1) gm_kernels::reg_launch(P, grid, smem, stream);
         else gm_kernels::generic_launch(P, grid, block, smem, stream);
+    } else if (tier == 6) {
+        block = kHbmThreads;
+        P.hbm_layout = 1;
+        P.coop_G = G;
+        const int groups = std::min(P.count, d.sms / G);
+        grid = groups * G;
+        smem = cl.smem_bytes;
+        int per_sm = 0;
+        CK(gm_kernels::coop_occupancy(block, smem, &per_sm));
+        if (per_sm < 1) return GM_ERR_TOO_LARGE;
+        CK(cudaMallocAsync(&work, cl.group_doubles * sizeof(double) * groups, stream));
+        P.work = work;
+        P.work_stride = (long long)cl.group_doubles;
+        // the group barrier counters live behind the queue counter (zeroed above), 8-byte aligned
+        P.coop_bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(queue) + 8);
+        if (ev0) CK(cudaEventRecord(ev0, stream));
+        CK(gm_kernels::coop_launch(P, grid, block, smem, stream));
     } else {
         block = kHbmThreads;
         P.hbm_layout = 1;
         // per-CTA HBM slice: W only (tier 3), W + Bi (tier 4), everything (tier 5)
         const size_t per_cta = tier == 3 ? w3.Bi : (tier == 4 ? w2.big_doubles : (w2.big_doubles + w2.small_bytes / 8 + 8));
-        grid = (int)std::min<long long>(P.count, (long long)g.sms);
+        grid = (int)std::min<long long>(P.count, (long long)d.sms);
         CK(cudaMallocAsync(&work, per_cta * sizeof(double) * grid, stream));
         P.work = work;
         P.work_stride = (long long)per_cta;
@@ -124,9 +231,9 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
         } else if (tier == 4) {
             // TMA staging ring: up to 3 stages of 32 KB if they fit beside the vectors
             const size_t stage = 32768;
-            long long room = (long long)g.smem_optin - (long long)w2.small_bytes - 256;
+            long long room = (long long)d.smem_optin - (long long)w2.small_bytes - 256;
             int ns = (int)std::min<long long>(3, room / (long long)stage);
-            if (ns < 2 || g.opt.reserved == 1) ns = 0;  // options.reserved = 1 disables the ring (A/B measurements)
+            if (ns < 2 || opt.reserved == 1) ns = 0;  // options.reserved = 1 disables the ring (A/B measurements)
             P.ring_stages = ns;
             P.ring_stage_bytes = ns ? (int)stage : 0;
             P.stream_min_m = 384;
@@ -154,18 +261,28 @@ int launch_wave(gm::BatchParams P, cudaStream_t stream, cudaEvent_t ev0, cudaEve
     return GM_OK;
 }
 
-int root_lookup(gm_root_t h, const double** c, const double** A, const double** b, int* m0, int* n0) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    auto it = g.roots.find(h);
-    if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
-    *c = it->second.c; *A = it->second.A; *b = it->second.b;
-    *m0 = it->second.m0; *n0 = it->second.n0;
-    return GM_OK;
+// Called by the host-buffer entry points once their stream has been synchronised: brings an armed trace back.
+void finish_trace() {
+    if (!t_trace.in_flight) return;
+    t_trace.rows.assign((size_t)t_trace.cap * 4, -1);
+    cudaMemcpyAsync(t_trace.rows.data(), t_trace.d_buf, sizeof(int) * 4 * (size_t)t_trace.cap, cudaMemcpyDeviceToHost,
+                    t_trace.stream);
+    cudaStreamSynchronize(t_trace.stream);
+    cudaFreeAsync(t_trace.d_buf, t_trace.stream);
+    t_trace.in_flight = false;
+    t_trace.armed = false;
+    t_trace.d_buf = nullptr;
 }
 
-}  // namespace gm_internal
+float ms(cudaEvent_t a, cudaEvent_t b) {
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    return t;
+}
 
-using gm_internal::launch_wave;
+}  // namespace gm_engine
+
+using namespace gm_engine;
 
 extern "C" {
 
@@ -178,34 +295,15 @@ int gm_device_count(void) {
 const char* gm_last_error(void) { return t_err.c_str(); }
 
 int gm_init(int device) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        t_err = "no CUDA device (the engine has no CPU fallback)";
-        return GM_ERR_NO_DEVICE;
-    }
-    if (device < 0 || device >= n) return GM_ERR_BAD_ARGUMENT;
-    CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    g.device = device;
-    g.sms = prop.multiProcessorCount;
-    g.smem_optin = prop.sharedMemPerBlockOptin;
-    // keep stream-ordered allocations cached across calls (the default pool trims at every synchronize)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    g.ready = true;
-    return GM_OK;
+    const int rc = init_device(device);
+    if (rc == GM_OK) t_device = device;
+    return rc;
 }
 
 int gm_shutdown(void) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.ready) return GM_OK;
     for (auto& kv : g.roots) {
+        cudaSetDevice(kv.second.device);
         cudaFree(kv.second.c);
         cudaFree(kv.second.A);
         cudaFree(kv.second.b);
@@ -213,7 +311,17 @@ int gm_shutdown(void) {
         cudaFree(kv.second.prev_basis);
     }
     g.roots.clear();
-    g.ready = false;
+    for (int i = 0; i < kMaxDevices; ++i) {
+        DeviceCtx& d = g.dev[i];
+        if (!d.ready) continue;
+        cudaSetDevice(i);
+        std::lock_guard<std::mutex> lk2(d.mu);
+        for (auto* se : d.pool) delete se;
+        d.pool.clear();
+        d.ready = false;
+    }
+    g.default_device = -1;
+    t_device = -1;
     return GM_OK;
 }
 
@@ -230,10 +338,28 @@ int gm_last_timing(gm_timing* out) {
     return GM_OK;
 }
 
+int gm_trace_arm(int64_t lp_index, int64_t cap) {
+    if (lp_index < 0 || cap <= 0 || cap > (1 << 22)) return GM_ERR_BAD_ARGUMENT;
+    t_trace.armed = true;
+    t_trace.in_flight = false;
+    t_trace.lp = lp_index;
+    t_trace.cap = cap;
+    t_trace.rows.clear();
+    return GM_OK;
+}
+
+int64_t gm_trace_fetch(int32_t* out, int64_t cap) {
+    if (!out) return 0;
+    const int64_t rows = std::min<int64_t>(cap, (int64_t)t_trace.rows.size() / 4);
+    std::memcpy(out, t_trace.rows.data(), sizeof(int32_t) * 4 * (size_t)rows);
+    return rows;
+}
+
 int gm_simplex_batch_device(int64_t count, const double* d_c, const double* d_A, const double* d_b, int64_t m,
                             int64_t n, double tol, int32_t* d_status, double* d_optF, double* d_optX,
                             int64_t* d_basis, int32_t* d_stats, void* stream) {
-    int rc = ensure_ready();
+    DeviceCtx* d = nullptr;
+    int rc = current_device(&d);
     if (rc != GM_OK) return rc;
     if (count < 0 || m <= 0 || n <= 0 || count > INT32_MAX || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;
     if (!d_c || !d_A || !d_b || !d_status || !d_optF || !d_optX) return GM_ERR_BAD_ARGUMENT;
@@ -246,7 +372,11 @@ int gm_simplex_batch_device(int64_t count, const double* d_c, const double* d_A,
     P.status = d_status; P.optF = d_optF; P.x = d_optX; P.x_stride = n; P.x_len = (int)n;
     P.basis = reinterpret_cast<long long*>(d_basis); P.stats = d_stats;
     t_timing = gm_timing{};
-    return launch_wave(P, (cudaStream_t)stream, nullptr, nullptr, &t_timing);
+    const bool was_armed = t_trace.armed;
+    t_trace.armed = false;  // asynchronous entry point: a trace cannot be brought back
+    rc = launch_wave(*d, P, (cudaStream_t)stream, nullptr, nullptr, &t_timing);
+    t_trace.armed = was_armed;
+    return rc;
 }
 
 }  // extern "C"
@@ -259,34 +389,18 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, s); }
     template <class T> T* as() { return static_cast<T*>(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
 };
-struct StreamEvents {
-    cudaStream_t s = nullptr;
-    cudaEvent_t e[6] = {};
-    cudaError_t init() {
-        cudaError_t r = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-        for (int i = 0; i < 6 && r == cudaSuccess; ++i) r = cudaEventCreate(&e[i]);
-        return r;
-    }
-    ~StreamEvents() {
-        for (auto& ev : e) if (ev) cudaEventDestroy(ev);
-        if (s) cudaStreamDestroy(s);
-    }
-};
-float ms(cudaEvent_t a, cudaEvent_t b) {
-    float t = 0;
-    cudaEventElapsedTime(&t, a, b);
-    return t;
-}
 }  // namespace
 
 // shared body of the host-buffer entry points: per-LP roots (stride != 0) or wave over a device root
-static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A, int64_t h_lda, const double* h_b,
-                         const int64_t* h_ib, const int32_t* h_bvar, const double* h_bsign, const double* h_brhs,
-                         int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats,
-                         long long* d_basis_keep = nullptr) {
-    StreamEvents se;
-    CK(se.init());
+static int run_host_call(DeviceCtx& d, gm::BatchParams P, const double* h_c, const double* h_A, int64_t h_lda,
+                         const double* h_b, const int64_t* h_ib, const int32_t* h_bvar, const double* h_bsign,
+                         const double* h_brhs, int32_t* status, double* optF, double* optX, int64_t* basis,
+                         int32_t* stats) {
+    StreamLease lease(&d);
+    CK(lease.err);
+    StreamEvents& se = *lease.se;
     cudaStream_t st = se.s;
     const int64_t count = P.count, m0 = P.m0, n0 = P.n0, L = P.L, m = m0 + L;
     DevBuf dc(st), dA(st), db(st), dib(st), dbv(st), dbs(st), dbr(st), dst(st), dF(st), dX(st), dB(st), dS(st);
@@ -324,12 +438,11 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
     CK(dF.alloc(sizeof(double) * count));
     CK(dX.alloc(sizeof(double) * count * P.x_len));
     P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.x_stride = P.x_len;
-    if (d_basis_keep) P.basis = d_basis_keep;  // caller-owned device buffer (warm start keeps it for the next wave)
-    else if (basis) { CK(dB.alloc(sizeof(int64_t) * count * m)); P.basis = dB.as<long long>(); }
+    if (basis) { CK(dB.alloc(sizeof(int64_t) * count * m)); P.basis = dB.as<long long>(); }
     if (stats) { CK(dS.alloc(sizeof(int32_t) * count * 8)); P.stats = dS.as<int>(); }
     t_timing = gm_timing{};
-    int rc = launch_wave(P, st, se.e[1], se.e[2], &t_timing);
-    if (rc != GM_OK) { cudaStreamSynchronize(st); return rc; }
+    int rc = launch_wave(d, P, st, se.e[1], se.e[2], &t_timing);
+    if (rc != GM_OK) { cudaStreamSynchronize(st); finish_trace(); return rc; }
     CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(optF, dF.p, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(optX, dX.p, sizeof(double) * count * P.x_len, cudaMemcpyDeviceToHost, st));
@@ -337,6 +450,7 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
     if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * count * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(se.e[3], st));
     CK(cudaStreamSynchronize(st));
+    finish_trace();
     t_timing.h2d_ms = ms(se.e[0], se.e[1]);
     t_timing.kernel_ms = ms(se.e[1], se.e[2]);
     t_timing.d2h_ms = ms(se.e[2], se.e[3]);
@@ -346,26 +460,23 @@ static int run_host_call(gm::BatchParams P, const double* h_c, const double* h_A
 // Large host batches: the batch is cut in chunks; chunk k+1 crosses PCIe on the copy stream while chunk k is
 // being solved, and consecutive chunks are launched on alternating compute streams so that the tail of
 // one launch overlaps the head of the next. Same results as one launch (LPs are independent).
-static int run_host_batch_pipelined(gm::BatchParams P, const double* h_c, const double* h_A, const double* h_b,
-                                    int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats,
-                                    int chunks) {
+static int run_host_batch_pipelined(DeviceCtx& d, gm::BatchParams P, const double* h_c, const double* h_A,
+                                    const double* h_b, int32_t* status, double* optF, double* optX, int64_t* basis,
+                                    int32_t* stats, int chunks) {
     const int64_t count = P.count, m = P.m0, n = P.n0;
-    cudaStream_t cs = nullptr, ks[2] = {nullptr, nullptr};
+    StreamLease l0(&d), l1(&d), l2(&d);
+    CK(l0.err); CK(l1.err); CK(l2.err);
+    cudaStream_t cs = l0.se->s, ks[2] = {l1.se->s, l2.se->s};
     std::vector<cudaEvent_t> ev(3 * chunks + 2, nullptr);
     auto cleanup = [&]() {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        if (cs) cudaStreamDestroy(cs);
-        for (auto& k : ks) if (k) cudaStreamDestroy(k);
     };
 #define CKP(call)                                                 \
     do {                                                          \
         cudaError_t e_ = (call);                                  \
         if (e_ != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return fail(e_, #call); } \
     } while (0)
-    CKP(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    CKP(cudaStreamCreateWithFlags(&ks[0], cudaStreamNonBlocking));
-    CKP(cudaStreamCreateWithFlags(&ks[1], cudaStreamNonBlocking));
-    for (auto& e : ev) CKP(cudaEventCreate(&e));
+    for (auto& e : ev) CKP(cudaEventCreateWithFlags(&e, cudaEventDefault));
     double *dc = nullptr, *dA = nullptr, *db = nullptr, *dF = nullptr, *dX = nullptr;
     int32_t *dst = nullptr, *dS = nullptr;
     long long* dB = nullptr;
@@ -397,7 +508,7 @@ static int run_host_batch_pipelined(gm::BatchParams P, const double* h_c, const 
         Q.status = dst + off; Q.optF = dF + off; Q.x = dX + off * n; Q.x_stride = n;
         Q.basis = basis ? dB + off * m : nullptr;
         Q.stats = stats ? dS + off * 8 : nullptr;
-        rc = launch_wave(Q, st, ev[3 * k + 1], ev[3 * k + 2], &t_timing);
+        rc = launch_wave(d, Q, st, ev[3 * k + 1], ev[3 * k + 2], &t_timing);
         if (rc != GM_OK) break;
     }
     // results come back in one piece at the end: a device->host copy into pageable memory (a Go slice, a numpy
@@ -435,7 +546,8 @@ extern "C" {
 
 int gm_simplex_batch(int64_t count, const double* c, const double* A, const double* b, int64_t m, int64_t n,
                      double tol, int32_t* status, double* optF, double* optX, int64_t* basis, int32_t* stats) {
-    int rc = ensure_ready();
+    DeviceCtx* d = nullptr;
+    int rc = current_device(&d);
     if (rc != GM_OK) return rc;
     if (count < 0 || m <= 0 || n <= 0 || count > INT32_MAX || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;
     if (count == 0) return GM_OK;
@@ -446,15 +558,16 @@ int gm_simplex_batch(int64_t count, const double* c, const double* A, const doub
     P.m0 = (int)m; P.n0 = (int)n; P.L = 0; P.tol = tol; P.count = (int)count; P.x_len = (int)n;
     // pipeline when the input is big enough for PCIe time to matter and every chunk still fills the GPU
     const double in_bytes = (double)count * (double)(m * n + m + n) * 8.0;
-    int chunks = (int)std::min<int64_t>(8, count / (4 * (int64_t)g.sms));
-    if (in_bytes < 32e6) chunks = 1;
-    if (chunks >= 2) return run_host_batch_pipelined(P, c, A, b, status, optF, optX, basis, stats, chunks);
-    return run_host_call(P, c, A, n, b, nullptr, nullptr, nullptr, nullptr, status, optF, optX, basis, stats);
+    int chunks = (int)std::min<int64_t>(8, count / (4 * (int64_t)d->sms));
+    if (in_bytes < 32e6 || t_trace.armed) chunks = 1;
+    if (chunks >= 2) return run_host_batch_pipelined(*d, P, c, A, b, status, optF, optX, basis, stats, chunks);
+    return run_host_call(*d, P, c, A, n, b, nullptr, nullptr, nullptr, nullptr, status, optF, optX, basis, stats);
 }
 
 int gm_simplex(const double* c, const double* A, int64_t lda, const double* b, int64_t m, int64_t n, double tol,
                const int64_t* initialBasic, double* optF, double* optX, int64_t* basisOut, int64_t* pivots) {
-    int rc = ensure_ready();
+    DeviceCtx* d = nullptr;
+    int rc = current_device(&d);
     if (rc != GM_OK) return rc;
     if (m <= 0 || n <= 0 || lda < n || m > (1 << 20) || n > (1 << 20)) return GM_ERR_BAD_SHAPE;  // simplex.go:387-398 panics
     if (!c || !A || !b || !optF || !optX) return GM_ERR_BAD_ARGUMENT;
@@ -464,7 +577,7 @@ int gm_simplex(const double* c, const double* A, int64_t lda, const double* b, i
     P.m0 = (int)m; P.n0 = (int)n; P.L = 0; P.tol = tol; P.count = 1; P.x_len = (int)n;
     int32_t status = GM_ERR_CUDA;
     int32_t stats[8] = {0};
-    rc = run_host_call(P, c, A, lda, b, initialBasic, nullptr, nullptr, nullptr, &status, optF, optX, basisOut, stats);
+    rc = run_host_call(*d, P, c, A, lda, b, initialBasic, nullptr, nullptr, nullptr, &status, optF, optX, basisOut, stats);
     if (rc != GM_OK) return rc;
     if (pivots) *pivots = (int64_t)stats[0] + stats[1];
     return status;
@@ -472,18 +585,29 @@ int gm_simplex(const double* c, const double* A, int64_t lda, const double* b, i
 
 int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
                    gm_root_t* out) {
-    int rc = ensure_ready();
+    DeviceCtx* d = nullptr;
+    int rc = current_device(&d);
     if (rc != GM_OK) return rc;
     if (m0 <= 0 || n0 <= 0 || lda < n0) return GM_ERR_BAD_SHAPE;
     if (!c0 || !A0 || !b0 || !out) return GM_ERR_BAD_ARGUMENT;
+    StreamLease lease(d);
+    CK(lease.err);
+    cudaStream_t st = lease.se->s;
+    DevBuf dc(st), dA(st), db(st);
+    CK(dc.alloc(sizeof(double) * n0));
+    CK(dA.alloc(sizeof(double) * m0 * n0));
+    CK(db.alloc(sizeof(double) * m0));
+    CK(cudaMemcpyAsync(dc.p, c0, sizeof(double) * n0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(dA.p, sizeof(double) * n0, A0, sizeof(double) * lda, sizeof(double) * n0, m0,
+                         cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db.p, b0, sizeof(double) * m0, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the caller's buffers are not retained past the return (cgo pointer rule)
     Root r;
+    r.device = d->id;
     r.m0 = (int)m0; r.n0 = (int)n0;
-    CK(cudaMalloc(&r.c, sizeof(double) * n0));
-    CK(cudaMalloc(&r.A, sizeof(double) * m0 * n0));
-    CK(cudaMalloc(&r.b, sizeof(double) * m0));
-    CK(cudaMemcpy(r.c, c0, sizeof(double) * n0, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy2D(r.A, sizeof(double) * n0, A0, sizeof(double) * lda, sizeof(double) * n0, m0, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(r.b, b0, sizeof(double) * m0, cudaMemcpyHostToDevice));
+    r.c = static_cast<double*>(dc.release());
+    r.A = static_cast<double*>(dA.release());
+    r.b = static_cast<double*>(db.release());
     std::lock_guard<std::mutex> lk(g.mu);
     *out = g.next_root++;
     g.roots[*out] = r;
@@ -491,78 +615,84 @@ int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double
 }
 
 int gm_free_root(gm_root_t root) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    auto it = g.roots.find(root);
-    if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
-    cudaFree(it->second.c);
-    cudaFree(it->second.A);
-    cudaFree(it->second.b);
-    cudaFree(it->second.prev_bi);
-    cudaFree(it->second.prev_basis);
-    g.roots.erase(it);
+    Root r;
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        auto it = g.roots.find(root);
+        if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
+        r = it->second;
+        g.roots.erase(it);
+    }
+    cudaSetDevice(r.device);
+    cudaFree(r.c);
+    cudaFree(r.A);
+    cudaFree(r.b);
+    cudaFree(r.prev_bi);
+    cudaFree(r.prev_basis);
+    if (t_device >= 0) cudaSetDevice(t_device);
     return GM_OK;
 }
 
 int gm_solve_wave(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
                   const double* brhs, int32_t* status, double* z, double* x, int64_t* basis, int32_t* stats) {
-    int rc = ensure_ready();
-    if (rc != GM_OK) return rc;
     if (nodes < 0 || L < 0 || nodes > INT32_MAX) return GM_ERR_BAD_SHAPE;
     if (nodes == 0) return GM_OK;
     if (!status || !z || !x || (L > 0 && (!bvar || !bsign || !brhs))) return GM_ERR_BAD_ARGUMENT;
+    Root r;
+    DeviceCtx* d = nullptr;
+    int rc = device_of_root(root, &r, &d);
+    if (rc != GM_OK) return rc;
     gm::BatchParams P;
     std::memset(&P, 0, sizeof(P));
-    int m0, n0;
-    rc = gm_internal::root_lookup(root, &P.c, &P.A, &P.b, &m0, &n0);
-    if (rc != GM_OK) return rc;
+    P.c = r.c; P.A = r.A; P.b = r.b;
+    const int m0 = r.m0, n0 = r.n0;
     for (int64_t i = 0; i < nodes * L; ++i)
         if (bvar[i] < 0 || bvar[i] >= n0) return GM_ERR_BAD_ARGUMENT;
     P.m0 = m0; P.n0 = n0; P.lda = n0; P.L = (int)L; P.tol = 0.0;  // subproblem.go:154,172 pass tol = 0
     P.count = (int)nodes; P.x_len = n0;
-    return run_host_call(P, nullptr, nullptr, 0, nullptr, nullptr, bvar, bsign, brhs, status, z, x, basis, stats);
+    return run_host_call(*d, P, nullptr, nullptr, 0, nullptr, nullptr, bvar, bsign, brhs, status, z, x, basis, stats);
 }
 
 int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* bvar, const double* bsign,
                        const double* brhs, const int32_t* parent, int32_t* status, double* z, double* x,
                        int64_t* basis, int32_t* stats) {
-    int rc = ensure_ready();
-    if (rc != GM_OK) return rc;
     if (nodes < 0 || L < 0 || nodes > INT32_MAX) return GM_ERR_BAD_SHAPE;
     if (nodes == 0) return GM_OK;
     if (!status || !z || !x || (L > 0 && (!bvar || !bsign || !brhs))) return GM_ERR_BAD_ARGUMENT;
-    Root* r = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g.mu);
-        auto it = g.roots.find(root);
-        if (it == g.roots.end()) return GM_ERR_BAD_HANDLE;
-        r = &it->second;
-    }
-    const int m0 = r->m0, n0 = r->n0;
+    Root r;
+    DeviceCtx* d = nullptr;
+    int rc = device_of_root(root, &r, &d);
+    if (rc != GM_OK) return rc;
+    const int m0 = r.m0, n0 = r.n0;
     const int64_t m = m0 + L;
     for (int64_t i = 0; i < nodes * L; ++i)
         if (bvar[i] < 0 || bvar[i] >= n0) return GM_ERR_BAD_ARGUMENT;
-    const bool can_warm = parent && L >= 1 && r->prev_bi && r->prev_m == m - 1;
+    const bool can_warm = parent && L >= 1 && r.prev_bi && r.prev_m == m - 1;
     if (can_warm)
         for (int64_t i = 0; i < nodes; ++i)
-            if (parent[i] >= r->prev_nodes) return GM_ERR_BAD_ARGUMENT;
+            if (parent[i] >= r.prev_nodes) return GM_ERR_BAD_ARGUMENT;
 
-    StreamEvents se;
-    CK(se.init());
+    StreamLease lease(d);
+    CK(lease.err);
+    StreamEvents& se = *lease.se;
     cudaStream_t st = se.s;
     gm::BatchParams P;
     std::memset(&P, 0, sizeof(P));
-    P.c = r->c; P.A = r->A; P.b = r->b;
+    P.c = r.c; P.A = r.A; P.b = r.b;
     P.m0 = m0; P.n0 = n0; P.lda = n0; P.L = (int)L; P.tol = 0.0;  // subproblem.go:154,172 pass tol = 0
     P.count = (int)nodes; P.x_len = n0; P.x_stride = n0;
-    // this wave's bases / inverses stay on the device for the next wave (if they fit comfortably)
-    double* cur_bi = nullptr;
-    long long* cur_basis = nullptr;
+    // this wave's bases / inverses stay on the device for the next wave (if they fit comfortably); they are owned
+    // by DevBufs until the wave has succeeded, so that an early return can neither leak nor publish them
+    DevBuf cur_bi(st), cur_basis(st);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const size_t need = (size_t)nodes * (size_t)m * (size_t)m * 8 + (size_t)nodes * (size_t)m * 8;
-    if (need < free_b / 2) {  // stream-ordered pool: no device-wide synchronisation per wave
-        CK(cudaMallocAsync(&cur_bi, (size_t)nodes * m * m * 8, st));
-        CK(cudaMallocAsync(&cur_basis, (size_t)nodes * m * 8, st));
+    const bool keep = need < free_b / 2;
+    if (keep) {  // stream-ordered pool: no device-wide synchronisation per wave
+        CK(cur_bi.alloc((size_t)nodes * m * m * 8));
+        CK(cur_basis.alloc((size_t)nodes * m * 8));
+        // a node that never writes its basis must read as "no basis" (-1) to the next wave
+        CK(cudaMemsetAsync(cur_basis.p, 0xff, (size_t)nodes * m * 8, st));
     }
     DevBuf dbv(st), dbs(st), dbr(st), dpar(st), dst(st), dF(st), dX(st), dB(st), dS(st), dlist(st);
     CK(cudaEventRecord(se.e[0], st));
@@ -579,22 +709,23 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
         CK(dpar.alloc(sizeof(int32_t) * nodes));
         CK(cudaMemcpyAsync(dpar.p, parent, sizeof(int32_t) * nodes, cudaMemcpyHostToDevice, st));
         P.warm_parent = dpar.as<int>();
-        P.warm_basis = r->prev_basis;
-        P.warm_bi = r->prev_bi;
+        P.warm_basis = r.prev_basis;
+        P.warm_bi = r.prev_bi;
     }
     CK(dst.alloc(sizeof(int32_t) * nodes));
     CK(dF.alloc(sizeof(double) * nodes));
     CK(dX.alloc(sizeof(double) * nodes * n0));
     CK(dS.alloc(sizeof(int32_t) * nodes * 8));
     P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.stats = dS.as<int>();
-    if (cur_basis) P.basis = cur_basis;
+    if (keep) P.basis = cur_basis.as<long long>();
     else if (basis) { CK(dB.alloc(sizeof(int64_t) * nodes * m)); P.basis = dB.as<long long>(); }
-    P.bi_out = cur_bi;
+    P.bi_out = keep ? cur_bi.as<double>() : nullptr;
     t_timing = gm_timing{};
-    rc = launch_wave(P, st, se.e[1], se.e[2], &t_timing);
+    rc = launch_wave(*d, P, st, se.e[1], se.e[2], &t_timing);
     if (rc == GM_OK) {
         CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * nodes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        finish_trace();
         t_timing.kernel_ms = ms(se.e[1], se.e[2]);
         // nodes whose warm start died are re-solved from scratch, in place, by a second launch
         std::vector<int> retry;
@@ -607,7 +738,7 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
             Q.warm_parent = nullptr;
             Q.lp_list = dlist.as<int>();
             Q.count = (int)retry.size();
-            rc = launch_wave(Q, st, se.e[3], se.e[4], &t_timing);
+            rc = launch_wave(*d, Q, st, se.e[3], se.e[4], &t_timing);
             if (rc == GM_OK) {
                 CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * nodes, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -621,13 +752,20 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
         if (basis) CK(cudaMemcpyAsync(basis, P.basis, sizeof(int64_t) * nodes * m, cudaMemcpyDeviceToHost, st));
         if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * nodes * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (r->prev_bi) cudaFreeAsync(r->prev_bi, st);
-    if (r->prev_basis) cudaFreeAsync(r->prev_basis, st);
     cudaStreamSynchronize(st);
-    r->prev_bi = cur_bi;
-    r->prev_basis = cur_basis;
-    r->prev_nodes = cur_bi ? nodes : 0;
-    r->prev_m = (int)m;
+    // publish this wave's state for the children only when it is complete; otherwise the root goes cold
+    std::lock_guard<std::mutex> lk(g.mu);
+    auto it = g.roots.find(root);
+    if (it != g.roots.end()) {
+        Root& rr = it->second;
+        if (rr.prev_bi) cudaFreeAsync(rr.prev_bi, st);
+        if (rr.prev_basis) cudaFreeAsync(rr.prev_basis, st);
+        const bool pub = rc == GM_OK && keep;
+        rr.prev_bi = pub ? static_cast<double*>(cur_bi.release()) : nullptr;
+        rr.prev_basis = pub ? static_cast<long long*>(cur_basis.release()) : nullptr;
+        rr.prev_nodes = pub ? nodes : 0;
+        rr.prev_m = (int)m;
+    }
     return rc;
 }
 

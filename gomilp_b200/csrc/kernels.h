@@ -14,4 +14,11 @@ cudaError_t reg_prepare(size_t smem, int* ctas_per_sm);
 void reg_launch(const gm::BatchParams& P, int grid, size_t smem, cudaStream_t st);
 cudaError_t generic_prepare(int block, size_t smem, int* ctas_per_sm);
 void generic_launch(const gm::BatchParams& P, int grid, int block, size_t smem, cudaStream_t st);
+// tier 6 (kernels_coop.cu): cooperative launch, `P.coop_G` CTAs per LP
+cudaError_t coop_prepare(size_t smem_max);
+cudaError_t coop_occupancy(int block, size_t smem, int* ctas_per_sm);
+cudaError_t coop_launch(const gm::BatchParams& P, int grid, int block, size_t smem, cudaStream_t st);
+// every kernel's dynamic shared-memory limit is raised once per device (gm_init), never per launch
+cudaError_t reg_set_smem_limit(size_t smem_max);
+cudaError_t generic_set_smem_limit(size_t smem_max);
 }  // namespace gm_kernels

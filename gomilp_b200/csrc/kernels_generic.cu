@@ -32,9 +32,10 @@ __global__ void __launch_bounds__(gm_kernels::kHbmThreads, 1) simplex_wave_gener
 }  // namespace
 
 namespace gm_kernels {
+cudaError_t generic_set_smem_limit(size_t smem_max) {
+    return cudaFuncSetAttribute(simplex_wave_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+}
 cudaError_t generic_prepare(int block, size_t smem, int* ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(simplex_wave_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_generic, block, smem);
 }
 void generic_launch(const gm::BatchParams& P, int grid, int block, size_t smem, cudaStream_t st) {

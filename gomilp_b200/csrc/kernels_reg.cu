@@ -19,15 +19,16 @@ __global__ void __launch_bounds__(gm_kernels::kSmemThreads, 2) simplex_wave_reg_
 }  // namespace
 
 namespace gm_kernels {
+cudaError_t reg_set_smem_limit(size_t smem_max) {
+    cudaError_t e = cudaFuncSetAttribute(simplex_wave_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(simplex_wave_reg_warm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+}
 cudaError_t reg_prepare(size_t smem, int* ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(simplex_wave_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(simplex_wave_reg_warm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_reg, kSmemThreads, smem);
 }
 void reg_launch(const gm::BatchParams& P, int grid, size_t smem, cudaStream_t st) {
-    if (P.warm_parent || P.bi_out) simplex_wave_reg_warm<<<grid, kSmemThreads, smem, st>>>(P);
+    if (P.warm_parent || P.bi_out || P.trace) simplex_wave_reg_warm<<<grid, kSmemThreads, smem, st>>>(P);
     else simplex_wave_reg<<<grid, kSmemThreads, smem, st>>>(P);
 }
 }  // namespace gm_kernels

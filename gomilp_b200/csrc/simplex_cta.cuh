@@ -77,6 +77,13 @@ struct BatchParams {
     long long work_stride;  // doubles per CTA
     int* queue;             // work-queue counter (zeroed before launch)
     const int* lp_list;     // optional: work item k solves LP lp_list[k] (retry launches); nullptr = identity
+    // ---- pivot trace (parity evidence): LP `trace_lp` records (phase, entering variable, leaving variable, bland)
+    // for its first `trace_cap` pivots. Only the WARM-capable kernels carry the code (the bench kernel does not).
+    int* trace;
+    int trace_cap, trace_lp;
+    // ---- cooperative tier (6): `coop_G` CTAs of one cooperative launch work on one LP (simplex_wave_coop) --------
+    int coop_G;                     // CTAs per group
+    unsigned long long* coop_bar;   // [groups] barrier counters, zeroed before launch
 };
 
 // Workspace of one CTA, split in a "big" part (W and Bi: O(mn) doubles) and a "small" part (vectors,
@@ -158,9 +165,46 @@ struct MinLoc {
     int i;
 };
 
+// Cooperative tier: what one group of G CTAs keeps in HBM after the generic workspace (ws_layout with hbm = true),
+// and what each of its CTAs keeps in shared memory. Offsets in doubles.
+struct CoopLayout {
+    size_t Bi1, Tp, Rs, mail, group_doubles;              // HBM, relative to the group's slice
+    size_t s_y, s_prow, s_ae, s_xb, s_al, s_f, s_r, s_part, s_red, s_bit, s_redi, smem_bytes;  // shared memory
+};
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline CoopLayout coop_layout(int m, int n, int T, int G) {
+    const WsLayout w = ws_layout(m, n, T, false, true);
+    CoopLayout c;
+    auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+    size_t o = up4(w.big_doubles + w.small_bytes / 8 + 8);
+    c.Bi1 = o; o = up4(o + (size_t)m * w.ldb);
+    c.Tp = o; o = up4(o + (size_t)m * 32);
+    c.Rs = o; o = up4(o + (size_t)32 * w.ldb);
+    c.mail = o; o = up4(o + 16 + 8 * (size_t)G);
+    c.group_doubles = o;
+    const size_t mp = (size_t)((m + 3) & ~3);
+    const size_t rlen = (size_t)(((n + 1 - m) > m ? (n + 1 - m) : m) + 4) & ~(size_t)3;
+    size_t q = 0;
+    c.s_y = q; q += mp;
+    c.s_prow = q; q += mp;
+    c.s_ae = q; q += mp;
+    c.s_xb = q; q += mp;
+    c.s_al = q; q += mp;
+    c.s_f = q; q += mp;
+    c.s_r = q; q += rlen;
+    c.s_part = q; q += (size_t)T + mp;
+    c.s_red = q; q += (size_t)T;
+    c.s_bit = q; q += (mp + 1) / 2;     // ints
+    c.s_redi = q; q += ((size_t)T + 1) / 2;  // ints
+    c.smem_bytes = q * sizeof(double);
+    return c;
+}
+
 // WARM = compiled with the warm-start entry / basis-inverse output paths (gm_solve_wave_warm); the cold
 // instantiation of the register tier is kept free of them because they cost registers in the hot loop.
-template <bool REG, bool WARM = true>
+template <bool REG, bool WARM = true, bool COOP = false>
 struct SolverT {
     // problem
     int m, n, m0, n0, L, lda;
@@ -187,6 +231,29 @@ struct SolverT {
     // counters (uniform across the CTA)
     int piv1, piv2, nbland, ninv, used_p1, scan_fb, nrepair;
     int max_pivots, refactor_period;
+    // pivot trace of one LP (nullptr: off); cur_phase / cur_bland describe the pivot being made
+    int* trace_out;
+    int trace_cap, cur_phase, cur_bland;
+    // ---- cooperative tier: this CTA is `rank` of `G` CTAs that share one LP (state in HBM, see coop_loop) -------
+    int G, rank;
+    unsigned long long* gbar;     // the group's barrier counter
+    unsigned long long epoch;     // barriers passed so far
+    double* mail;                 // the group's mailbox: command, arguments, per-CTA argmin records
+    double *Bi1, *Tp, *Rs;        // second buffer of the inverse; inversion panel (m x CNB) and pivot-row snapshot
+    double *s_y, *s_prow, *s_ae, *s_xb, *s_al, *s_f, *s_r, *s_part;  // shared-memory scratch of this CTA
+    int* s_bit;
+
+    GM_DEV void trace_pivot(int enter_var, int leave_var) {  // called by ONE thread, before the counters move
+        if constexpr (WARM) {
+            if (trace_out) {
+                const int k = piv1 + piv2;
+                if (k < trace_cap) {
+                    int* rr = trace_out + 4 * k;
+                    rr[0] = cur_phase; rr[1] = enter_var; rr[2] = leave_var; rr[3] = cur_bland;
+                }
+            }
+        }
+    }
 
     GM_DEV static int pow2ceil(int v) {
         int p = 1;
@@ -632,6 +699,7 @@ struct SolverT {
     // under which LU.Solve reports mat.Condition, lu.go:301,321). *cond1 = ||B||_1 * ||B^-1||_1.
     GM_DEV int invert_basis(double* cond1) {
         if constexpr (REG) return invert_basis_reg(cond1);
+        if constexpr (COOP) return invert_basis_coop(cond1);
         const int t = gm_tid(), T = gm_nthreads();
         ninv++;
         for_each_2d(m, m, [&](int i, int j) { Bi[(size_t)i * ldb + j] = W[(size_t)i * ldw + j]; });
@@ -749,7 +817,6 @@ struct SolverT {
             const int p = idx;
             double f = gm_shfl_idx(sel, (lane & ~3) | kq);  // my row's entry in column k
             if (row == p) {
-#pragma unroll
                 const double inv = 1.0 / f;
 #pragma unroll
                 for (int jj = 0; jj < (REG ? 16 : 1); ++jj) {
@@ -995,13 +1062,64 @@ struct SolverT {
         return GM_OK;
     }
 
+    // ---- condition number of the basis with position p replaced by the column staged in t1 -----------------
+    // (al = Bi t1 must be current.) The reference factorises the swapped basis from scratch and takes LAPACK's
+    // estimate: replaceBland tests mat.Cond(swapped, 1) < 1e16 (simplex.go:369-379), the Phase-I repair loop accepts
+    // a column iff LU.Solve does not report mat.Condition, i.e. cond_inf <= 1e16 (simplex.go:589-605, lu.go:301,321).
+    // Here both norms are exact: ||B'||.||B'^-1|| with B'^-1 = E Bi read off the product-form update (O(m^2), no
+    // factorisation). inf_norm selects the infinity norm, else the 1-norm.
+    GM_DEV double swapped_cond(int p, bool inf_norm) {
+        if constexpr (REG) reg_dump();
+        const double ap = al[p];
+        if (!(fabs(ap) > 0.0) || ap != ap) return INFINITY;  // exactly singular: Dgetrf's zero pivot, cond = +Inf
+        const double inv = 1.0 / ap;
+        double ninv, nb;
+        if (!inf_norm) {
+            ninv = block_max(m, [&](int j) {
+                const double pj = Bi[(size_t)p * ldb + j] * inv;
+                double sum = fabs(pj);
+                for (int i = 0; i < m; ++i)
+                    if (i != p) sum += fabs(Bi[(size_t)i * ldb + j] - al[i] * pj);
+                return sum;
+            });
+            nb = block_max(m, [&](int q) {
+                double sum = 0;
+                if (q == p) {
+                    for (int i = 0; i < m; ++i) sum += fabs(t1[i]);
+                } else {
+                    const int cq = wcol_b(q);
+                    for (int i = 0; i < m; ++i) sum += fabs(W[(size_t)i * ldw + cq]);
+                }
+                return sum;
+            });
+        } else {
+            ninv = block_max(m, [&](int i) {
+                const double f = al[i] * inv;
+                double sum = 0;
+                for (int j = 0; j < m; ++j) {
+                    const double pj = Bi[(size_t)p * ldb + j];
+                    sum += fabs(i == p ? pj * inv : Bi[(size_t)i * ldb + j] - f * pj);
+                }
+                return sum;
+            });
+            nb = block_max(m, [&](int i) {
+                double sum = fabs(t1[i]);
+                for (int q = 0; q < m; ++q)
+                    if (q != p) sum += fabs(W[(size_t)i * ldw + wcol_b(q)]);
+                return sum;
+            });
+        }
+        return ninv * nb;
+    }
+
     // ---- replaceBland, simplex.go:347-383 -----------------------------------------------------------
-    // The reference accepts a zero-step leaving position only if the swapped basis has cond_1 < 1e16.
-    // Here the test is on the pivot element: a finite ratio already implies |d_p| >= 1e-13 (dRoundTol),
-    // and the product-form update divides by d_p only, so the position is taken when |d_p| is not
-    // negligible against the column (|d_p| > 1e-11 * max|d|).
-    GM_DEV int replace_bland(int& l_out, int& e_out) {
+    // Candidates are the non-basic positions with r <= -blandNegTol in list order; the first whose ratio test gives a
+    // non-zero step wins, else the first zero-step leaving position whose swapped basis has cond_1 < 1e16 (exact
+    // norms, see swapped_cond). `weak` reports a pivot element at noise level against its column: the caller
+    // rebuilds the inverse right after the pivot so that the product form does not carry the division by it.
+    GM_DEV int replace_bland(int& l_out, int& e_out, bool& weak) {
         int from = 0;
+        weak = false;
         for (;;) {
             const int i = block_min_int(nn - from, [&](int q) { return r[from + q] <= -GM_BLAND_NEG_TOL ? from + q : INT_MAX; });
             if (i == INT_MAX) return GM_ERR_BLAND;
@@ -1010,10 +1128,18 @@ struct SolverT {
             MinLoc ml = block_argmin(m, [&](int q) { return mv[q]; });
             if (fabs(ml.v) > GM_BLAND_ZERO_TOL) { l_out = ml.i; e_out = i; return GM_OK; }
             const double dmax = block_max(m, [&](int q) { return fabs(al[q]); });
-            const int p = block_min_int(m, [&](int q) {
-                return (mv[q] <= GM_BLAND_ZERO_TOL && fabs(al[q]) > 1e-11 * dmax) ? q : INT_MAX;
-            });
-            if (p != INT_MAX) { l_out = p; e_out = i; return GM_OK; }
+            int pfrom = 0;
+            for (;;) {
+                const int p = block_min_int(m - pfrom, [&](int q) { return mv[pfrom + q] <= GM_BLAND_ZERO_TOL ? pfrom + q : INT_MAX; });
+                if (p == INT_MAX) break;
+                if (swapped_cond(p, false) < GM_CONDITION_TOL) {
+                    l_out = p; e_out = i;
+                    weak = !(fabs(al[p]) > 1e-9 * dmax);
+                    return GM_OK;
+                }
+                pfrom = p + 1;
+                if (pfrom >= m) break;
+            }
             from = i + 1;
             if (from >= nn) return GM_ERR_BLAND;
         }
@@ -1034,6 +1160,7 @@ struct SolverT {
         }
         if (t == 0) {
             const int v = basic[l];
+            trace_pivot(nonbasic[e], v);
             basic[l] = nonbasic[e];
             nonbasic[e] = v;
             const double cc = cb[l];
@@ -1055,6 +1182,7 @@ struct SolverT {
     // (last iterate is still reported, simplex.go:294-301).
     GM_DEV int main_loop(double tol, int phase, bool fresh) {
         if constexpr (REG) return main_loop_reg(tol, phase, fresh);
+        if constexpr (COOP) return main_loop_coop(tol, phase, fresh);
         if (bi_smem && gm_nthreads() <= 1024) return main_loop_quad(tol, phase, fresh);
         if (ring != nullptr && m >= stream_min_m && (nn + 2) <= 8 * gm_nthreads() && ((n + 3) & ~1) <= ring_stage_doubles &&
             ((m + 1) & ~1) <= ring_stage_doubles)
@@ -1088,11 +1216,16 @@ struct SolverT {
             int l = ml.i;
             if (ml.v <= 0.0) {  // :268-277
                 nbland++;
-                rc = replace_bland(l, e);
+                bool weak;
+                rc = replace_bland(l, e, weak);
                 if (rc != GM_OK) return rc;
                 re = r[e];
+                if (weak) since = refactor_period;
+                cur_bland = 1;
             }
+            cur_phase = phase;
             pivot(l, e, re);
+            cur_bland = 0;
             if (phase == 1) piv1++; else piv2++;
             fresh = false;
             if (++since >= refactor_period) {
@@ -1238,10 +1371,13 @@ struct SolverT {
                 nbland++;
                 if (q == 0 && row < m) { al[row] = alpha; }
                 store_state();
-                const int rc = replace_bland(l, e);
+                bool weak;
+                const int rc = replace_bland(l, e, weak);
                 if (rc != GM_OK) return rc;
                 re = r[e];
                 alpha = row < m ? al[row] : 0.0;
+                if (weak) since = refactor_period;
+                if constexpr (WARM) cur_bland = 1;
             }
             // ---- basis change (:280-292)
             if (row == l) {
@@ -1267,6 +1403,7 @@ struct SolverT {
             if (warp == ((e & 63) >> 3)) {
                 if (lane == 0) {
                     const int v = basic[l];
+                    if constexpr (WARM) { cur_phase = phase; trace_pivot(nonbasic[e], v); }
                     basic[l] = nonbasic[e];
                     nonbasic[e] = v;
                     const double cc = cb[l];
@@ -1275,6 +1412,7 @@ struct SolverT {
                 }
                 gm_syncwarp();
             }
+            if constexpr (WARM) cur_bland = 0;
             if (phase == 1) piv1++; else piv2++;
             fresh = false;
             if (++since >= refactor_period) {
@@ -1331,7 +1469,9 @@ struct SolverT {
             if (k + ring_ns < ntiles) issue(k + ring_ns);
         }
         ring_uses = use0 + ntiles;
-        return ok;
+        // a bounded wait that gave up on some threads only must not split the CTA: agree on the verdict
+        const int bad = block_min_int(gm_nthreads(), [&](int k) { return (k == t && !ok) ? 0 : INT_MAX; });
+        return bad == INT_MAX;
     }
 
     // Builds sel[] = ascending list of i in [0, count) with pred(i); returns its length (ballot compaction).
@@ -1419,10 +1559,14 @@ struct SolverT {
             int l = ml.i;
             if (ml.v <= 0.0) {  // :268-277
                 nbland++;
-                rc = replace_bland(l, e);
+                bool weak;
+                rc = replace_bland(l, e, weak);
                 if (rc != GM_OK) return rc;
                 re = r[e];
+                if (weak) since = refactor_period;
+                cur_bland = 1;
             }
+            cur_phase = phase;
             // ---- basis change: only the rows with alpha_i != 0 move
             {
                 const double ap = al[l];
@@ -1455,6 +1599,7 @@ struct SolverT {
                 }
                 if (t == 0) {
                     const int v = basic[l];
+                    trace_pivot(nonbasic[e], v);
                     basic[l] = nonbasic[e];
                     nonbasic[e] = v;
                     const double cc = cb[l];
@@ -1463,6 +1608,7 @@ struct SolverT {
                 }
                 gm_sync();
             }
+            cur_bland = 0;
             if (phase == 1) piv1++; else piv2++;
             fresh = false;
             if (++since >= refactor_period) {
@@ -1651,10 +1797,14 @@ struct SolverT {
             if (mvv <= 0.0) {  // :268-277
                 nbland++;
                 gm_sync();
-                const int rc = replace_bland(l, e);
+                bool weak;
+                const int rc = replace_bland(l, e, weak);
                 if (rc != GM_OK) return rc;
                 re = r[e];
+                if (weak) since = refactor_period;
+                cur_bland = 1;
             }
+            cur_phase = phase;
             // ---- basis change (:280-292)
             const double ap = al[l];
             const double inv = 1.0 / ap;
@@ -1684,12 +1834,14 @@ struct SolverT {
             }
             if (t == 0) {
                 const int v = basic[l];
+                trace_pivot(nonbasic[e], v);
                 basic[l] = nonbasic[e];
                 nonbasic[e] = v;
                 const double cc = cb[l];
                 cb[l] = cn[e];
                 cn[e] = cc;
             }
+            cur_bland = 0;
             if (phase == 1) piv1++; else piv2++;
             fresh = false;
             gm_sync();  // (5)
@@ -1700,6 +1852,508 @@ struct SolverT {
                 since = 0;
             }
         }
+    }
+
+    // =================================================================================================
+    // Cooperative tier (COOP): G CTAs of ONE cooperative launch share one LP.
+    //
+    // Why: with fewer LPs than SMs (one large LP - BASELINE config 4 -, the narrow first waves of every B&B) one CTA
+    // per LP leaves the GPU idle and runs the pivot at one SM's bandwidth. Here rank 0 (the leader) runs the solver's
+    // control flow exactly as the other tiers do, on state that lives in HBM / L2, and hands the two O(m^2)-per-step
+    // pieces to the whole group:
+    //   coop_loop     the simplex main loop (simplex.go:233-293): pricing by column tiles of W, FTRAN / ratio test /
+    //                 rank-1 update by row blocks of the inverse; two group barriers per pivot
+    //   coop_invert   blocked Gauss-Jordan inversion, trailing updates on the FP64 tensor cores (DMMA)
+    // Helpers (rank > 0) sit in coop_helper_loop and execute what the leader posts in the group's mailbox.
+    // All decisions are computed redundantly from the same records, so the CTAs never disagree on control flow.
+    // =================================================================================================
+    static constexpr int CNB = 32;          // inversion panel width (a multiple of the 8-wide DMMA tile)
+    enum { CMD_EXIT = 0, CMD_MAIN = 1, CMD_INVERT = 2 };
+    enum { CR_OPT = 0, CR_UNBOUNDED = 1, CR_BLAND = 2, CR_REFACTOR = 3, CR_ITER = 4 };
+    // mailbox layout (doubles): [0] command, [1..9] arguments, [10] flag; then per-CTA records
+    static constexpr int MAIL_HDR = 16;
+    GM_DEV double* rec_a(int g) const { return mail + MAIL_HDR + 2 * g; }           // {value, position}
+    GM_DEV double* rec_b(int g) const { return mail + MAIL_HDR + 2 * G + 4 * g; }   // {ratio, row, alpha, buffer bit}
+    GM_DEV double* rec_n(int g) const { return mail + MAIL_HDR + 6 * G + 2 * g; }   // {inf-norm part, 1-norm part}
+
+    // Group barrier: every CTA of the group arrives, all earlier global writes of the group are visible afterwards.
+    GM_DEV void grp_sync() {
+        gm_sync();
+        if (G > 1) {
+            ++epoch;
+            if (gm_tid() == 0) {
+                gm_threadfence();
+                gm_atomic_add_u64(gbar, 1ull);
+                const unsigned long long target = epoch * (unsigned long long)G;
+                while (gm_ld_acquire_u64(gbar) < target) gm_spin_pause();
+                gm_threadfence();
+            }
+            gm_sync();
+        }
+    }
+
+    GM_DEV double* bi_buf(int bit) const { return bit ? Bi1 : Bi; }
+
+    // out[j] (shared memory, j < tw) = sum over rows i < nrows of f(i, M[i][c0 + j]); the tile is walked with lanes
+    // along the contiguous dimension and T / S row groups, partials combined through s_part. Ends with a barrier.
+    template <class F>
+    GM_DEV void col_tile_reduce(const double* M, int ld, int nrows, int c0, int tw, double* out, F f) {
+        const int t = gm_tid(), T = gm_nthreads();
+        int S = pow2ceil(tw > 0 ? tw : 1);
+        if (S > T) S = T;
+        const int RG = T / S, col = t % S, rg = t / S;
+        for (int cb0 = 0; cb0 < tw; cb0 += S) {
+            const int j = cb0 + col;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            if (j < tw) {
+                const double* cp = M + c0 + j;
+                int i = rg;
+                for (; i + 3 * RG < nrows; i += 4 * RG) {
+                    const double v0 = cp[(size_t)i * ld], v1 = cp[(size_t)(i + RG) * ld];
+                    const double v2 = cp[(size_t)(i + 2 * RG) * ld], v3 = cp[(size_t)(i + 3 * RG) * ld];
+                    a0 += f(i, v0); a1 += f(i + RG, v1); a2 += f(i + 2 * RG, v2); a3 += f(i + 3 * RG, v3);
+                }
+                for (; i < nrows; i += RG) a0 += f(i, cp[(size_t)i * ld]);
+            }
+            s_part[t] = (a0 + a1) + (a2 + a3);
+            gm_sync();
+            if (t < S && cb0 + t < tw) {
+                double acc = 0;
+                for (int g2 = 0; g2 < RG; ++g2) acc += s_part[g2 * S + t];
+                out[cb0 + t] = acc;
+            }
+            gm_sync();
+        }
+    }
+
+    // Rows [r0, r1) of the inverse: apply the pending rank-1 update (row := row - f * prow, the previous pivot row
+    // := prow) writing the OTHER buffer, and, fused in the same pass, alpha_i = row_i . a_e. One warp per
+    // (row, column chunk); a row with f == 0 is only read. with_dot = false: update only.
+    GM_DEV void coop_rows_pass(int r0, int nr, bool pending, int lprev, bool with_dot) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        int C = nr > 0 ? nw / nr : 1;
+        if (C < 1) C = 1;
+        int clen = (m + C - 1) / C;
+        clen = (clen + 31) & ~31;
+        const int npairs = nr * C;
+        for (int pr = warp; pr < npairs; pr += nw) {
+            const int ri = pr / C, ch = pr % C;
+            const int i = r0 + ri;
+            const int j0 = ch * clen, j1 = (j0 + clen < m) ? j0 + clen : m;
+            const int bit = s_bit[ri];
+            const double f = s_f[ri];
+            const bool is_l = pending && i == lprev;
+            const bool wr = pending && (is_l || f != 0.0);
+            const double* src = bi_buf(bit) + (size_t)i * ldb;
+            double* dst = bi_buf(bit ^ 1) + (size_t)i * ldb;
+            double a0 = 0, a1 = 0;
+            int j = j0 + lane;
+            for (; j + 32 < j1; j += 64) {
+                double v0 = src[j], v1 = src[j + 32];
+                if (wr) {
+                    v0 = is_l ? s_prow[j] : v0 - f * s_prow[j];
+                    v1 = is_l ? s_prow[j + 32] : v1 - f * s_prow[j + 32];
+                    dst[j] = v0; dst[j + 32] = v1;
+                }
+                if (with_dot) { a0 += v0 * s_ae[j]; a1 += v1 * s_ae[j + 32]; }
+            }
+            if (j < j1) {
+                double v0 = src[j];
+                if (wr) {
+                    v0 = is_l ? s_prow[j] : v0 - f * s_prow[j];
+                    dst[j] = v0;
+                }
+                if (with_dot) a0 += v0 * s_ae[j];
+            }
+            if (with_dot) {
+                double acc = a0 + a1;
+                for (int d = 16; d >= 1; d >>= 1) acc += gm_shfl_xor(acc, d);
+                if (lane == 0) s_part[pr] = acc;
+            }
+        }
+        gm_sync();
+        for (int ri = t; ri < nr; ri += T) {
+            if (with_dot) {
+                double acc = 0;
+                for (int ch = 0; ch < C; ++ch) acc += s_part[ri * C + ch];
+                s_al[ri] = acc;
+            }
+            if (pending && (r0 + ri == lprev || s_f[ri] != 0.0)) s_bit[ri] ^= 1;
+        }
+        gm_sync();
+    }
+
+    // The simplex main loop of the cooperative tier; every CTA of the group runs it with the same arguments.
+    // Returns why it stopped (CR_*). State on entry / exit: W, Bi (buffer 0), xb, y, lists, cb, cn in HBM.
+    // Per pivot:
+    //   pricing   my tile of the non-basic columns against the CTA-local copy of y      -> record A, group barrier
+    //   FTRAN     my rows of the inverse . a_e, FUSED with the previous pivot's rank-1 update of those rows
+    //             (each row is read once and written once per pivot: 2 m^2 + m (n - m) words)
+    //   ratio     first minimum over my rows                                            -> record B, group barrier
+    //   update    y, xb, the lists; the rank-1 update itself is deferred to the next FTRAN pass
+    // A row of the inverse lives in one of two buffers (s_bit): an update writes the other one, so the pivot row
+    // everybody reads is never overwritten in the same pivot and no third barrier is needed.
+    GM_DEV int coop_loop(double tol, int phase, bool& fresh, int& since, int& e_out) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int r0 = (int)(((long long)rank * m) / G), r1 = (int)(((long long)(rank + 1) * m) / G), nr = r1 - r0;
+        const int k0 = (int)(((long long)rank * nn) / G), k1 = (int)(((long long)(rank + 1) * nn) / G), tw = k1 - k0;
+        for (int i = t; i < m; i += T) s_y[i] = y[i];
+        for (int i = t; i < nr; i += T) { s_xb[i] = xb[r0 + i]; s_f[i] = 0.0; s_bit[i] = 0; s_al[i] = 0.0; }
+        gm_sync();
+        bool pending = false;
+        int lprev = -1, skip = -1, reason;
+        double skip_r = 0.0;
+        for (;;) {
+            if (piv1 + piv2 >= max_pivots) { reason = CR_ITER; break; }
+            // ---- pricing: r = cn - an^T y over my tile (:236-250)
+            col_tile_reduce(W, ldw, m, m + k0, tw, s_r, [&](int i, double v) { return s_y[i] * v; });
+            for (int k = t; k < tw; k += T) {
+                // the variable that just left the basis sits at position `skip`; its reduced cost is -r_e / alpha_l
+                // analytically (its column is being swapped into place by the row owners right now)
+                const double rk = (k0 + k == skip) ? skip_r : cn[k0 + k] - s_r[k];
+                s_r[k] = rk;
+                r[k0 + k] = fabs(rk) < GM_R_ROUND_TOL ? 0.0 : rk;  // rounded copy for Bland (:252-256)
+            }
+            gm_sync();
+            MinLoc rl = block_argmin(tw, [&](int k) { return s_r[k]; });
+            if (t == 0) {
+                double* ra = rec_a(rank);
+                const bool valid = tw > 0 && rl.v == rl.v;
+                ra[0] = valid ? rl.v : INFINITY;
+                ra[1] = valid ? (double)(k0 + rl.i) : -1.0;
+            }
+            grp_sync();  // (A)
+            MinLoc best = block_argmin(G, [&](int g) { return rec_a(g)[1] >= 0.0 ? rec_a(g)[0] : NAN; });
+            const double bestv = best.v;
+            const int besti = bestv == bestv ? (int)rec_a(best.i)[1] : -1;
+            if (besti < 0 || bestv >= -tol || (!fresh && bestv > -1e-9 * cscale)) { reason = CR_OPT; break; }
+            const int e = besti;
+            const double re = bestv;
+            // ---- entering column, then my rows: pending update + FTRAN + ratio test (:306-342, :268)
+            for (int i = t; i < m; i += T) s_ae[i] = W[(size_t)i * ldw + m + e];
+            gm_sync();
+            coop_rows_pass(r0, nr, pending, lprev, true);
+            pending = false;
+            MinLoc ml = block_argmin(nr, [&](int q) {
+                double d = -s_al[q];
+                if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+                return d < 0.0 ? s_xb[q] / fabs(d) : INFINITY;
+            });
+            if (t == 0) {
+                double* rb = rec_b(rank);
+                const bool valid = nr > 0 && ml.v == ml.v;
+                rb[0] = valid ? ml.v : INFINITY;
+                rb[1] = valid ? (double)(r0 + ml.i) : -1.0;
+                rb[2] = valid ? s_al[ml.i] : 0.0;
+                rb[3] = valid ? (double)s_bit[ml.i] : 0.0;
+            }
+            grp_sync();  // (B)
+            MinLoc bl = block_argmin(G, [&](int g) { return rec_b(g)[1] >= 0.0 ? rec_b(g)[0] : NAN; });
+            const double mvv = bl.v == bl.v ? bl.v : INFINITY;
+            if (mvv == INFINITY) { reason = CR_UNBOUNDED; break; }  // Min(d) >= 0 (:329-331)
+            if (mvv <= 0.0) { reason = CR_BLAND; e_out = e; break; }  // :268-277, decided by the leader
+            const int l = (int)rec_b(bl.i)[1];
+            const double alpha_l = rec_b(bl.i)[2];
+            const int bit_l = (int)rec_b(bl.i)[3];
+            // ---- basis change (:280-292)
+            const double inv = 1.0 / alpha_l, theta = mvv;
+            {
+                const double* prw = bi_buf(bit_l) + (size_t)l * ldb;
+                for (int j = t; j < m; j += T) s_prow[j] = prw[j] * inv;
+            }
+            gm_sync();
+            for (int j = t; j < m; j += T) s_y[j] += re * s_prow[j];
+            for (int q = t; q < nr; q += T) {
+                const int i = r0 + q;
+                const double a = s_al[q];
+                s_xb[q] = (i == l) ? theta : s_xb[q] - a * theta;
+                s_f[q] = a;
+                const double wl = W[(size_t)i * ldw + l];
+                W[(size_t)i * ldw + l] = s_ae[i];
+                W[(size_t)i * ldw + m + e] = wl;
+            }
+            if (rank == 0 && t == 0) {
+                const int v = basic[l];
+                cur_phase = phase; cur_bland = 0;
+                trace_pivot(nonbasic[e], v);
+                basic[l] = nonbasic[e];
+                nonbasic[e] = v;
+                const double cc = cb[l];
+                cb[l] = cn[e];
+                cn[e] = cc;
+            }
+            pending = true;
+            lprev = l;
+            skip = e;
+            skip_r = -re * inv;
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            gm_sync();
+            if (++since >= refactor_period) { reason = CR_REFACTOR; break; }
+        }
+        // ---- hand the state back: finish a deferred update, gather every row in buffer 0, store xb / y
+        if (pending) coop_rows_pass(r0, nr, true, lprev, false);
+        {
+            const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+            for (int q = warp; q < nr; q += nw) {
+                if (!s_bit[q]) continue;
+                const double* src = Bi1 + (size_t)(r0 + q) * ldb;
+                double* dst = Bi + (size_t)(r0 + q) * ldb;
+                for (int j = lane; j < m; j += 32) dst[j] = src[j];
+            }
+        }
+        for (int q = t; q < nr; q += T) xb[r0 + q] = s_xb[q];
+        if (rank == 0)
+            for (int j = t; j < m; j += T) y[j] = s_y[j];
+        grp_sync();
+        return reason;
+    }
+
+    // Leader side of the main loop: posts the loop to the group, handles the rare events itself.
+    GM_DEV int main_loop_coop(double tol, int phase, bool fresh) {
+        const int t = gm_tid();
+        int since = 0;
+        for (;;) {
+            if (t == 0) {
+                mail[0] = CMD_MAIN; mail[1] = tol; mail[2] = phase; mail[3] = fresh ? 1.0 : 0.0; mail[4] = since;
+                mail[5] = piv1; mail[6] = piv2; mail[7] = cscale; mail[8] = nn; mail[9] = ncols;
+            }
+            grp_sync();
+            int e = 0;
+            const int reason = coop_loop(tol, phase, fresh, since, e);
+            if (reason == CR_ITER) return GM_ERR_ITERATION_LIMIT;
+            if (reason == CR_UNBOUNDED) return GM_ERR_UNBOUNDED;
+            if (reason == CR_OPT) {
+                if (!fresh) {  // confirm optimality with fresh-quality xb and y, like the other tiers
+                    const int rc = polish();
+                    if (rc != GM_OK) return rc;
+                    fresh = true;
+                    continue;
+                }
+                return GM_OK;
+            }
+            if (reason == CR_REFACTOR) {
+                const int rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+                continue;
+            }
+            // CR_BLAND: the degenerate step is resolved by the leader alone on the state in HBM (:268-277)
+            nbland++;
+            int l = 0;
+            bool weak;
+            int rc = replace_bland(l, e, weak);
+            if (rc != GM_OK) return rc;
+            const double re = r[e];
+            cur_bland = 1;
+            cur_phase = phase;
+            pivot(l, e, re);
+            cur_bland = 0;
+            if (phase == 1) piv1++; else piv2++;
+            fresh = false;
+            if (weak || ++since >= refactor_period) {
+                rc = refactor();
+                if (rc != GM_OK) return rc;
+                fresh = true;
+                since = 0;
+            }
+        }
+    }
+
+    // ---- blocked Gauss-Jordan inversion of W[:, 0:m] into Bi, trailing updates by DMMA ---------------------------
+    // Same contract as invert_basis (stands in for LU.Factorize + Dgecon, lu.go:63-84). Per panel of CNB columns:
+    //   leader   unblocked Gauss-Jordan with first-max row pivoting (Idamax, dgetf2.go:43-45) on the m x CNB panel
+    //   all      row interchanges and pivot-row snapshot on my column strip, then
+    //            M[:, J] += (T[:, K] - I_K) R   for every column J outside the panel: an (m x CNB)(CNB x m) product on
+    //            the FP64 tensor cores, 8-row blocks dealt round-robin to the CTAs, 8-column tiles to the warps
+    // Runs in every CTA of the group; only the leader's return value / cond1 are used.
+    GM_DEV int coop_invert_body(double* cond1) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        const int r0 = (int)(((long long)rank * m) / G), r1 = (int)(((long long)(rank + 1) * m) / G), nr = r1 - r0;
+        double* M = Bi;
+        ninv++;
+        // copy my rows, norms of B: row sums of my rows, column sums of my column strip
+        for (int q = warp; q < nr; q += nw)
+            for (int j = lane; j < m; j += 32) M[(size_t)(r0 + q) * ldb + j] = W[(size_t)(r0 + q) * ldw + j];
+        grp_sync();
+        double anorm_inf, anorm_1, inorm_inf, inorm_1;
+        coop_norms(M, r0, nr, anorm_inf, anorm_1);
+        int singular = 0;
+        for (int kb = 0; kb < m; kb += CNB) {
+            const int nbk = m - kb < CNB ? m - kb : CNB;
+            if (rank == 0) {
+                for_each_2d(m, nbk, [&](int i, int q) { Tp[(size_t)i * CNB + q] = M[(size_t)i * ldb + kb + q]; });
+                gm_sync();
+                for (int q = 0; q < nbk && !singular; ++q) {
+                    const int k = kb + q;
+                    MinLoc pl = block_argmin(m - k, [&](int s2) { return -fabs(Tp[(size_t)(k + s2) * CNB + q]); });
+                    const int p = k + pl.i;
+                    const double pabs = -pl.v;
+                    if (!(pabs > 0.0) || pabs == INFINITY) { singular = 1; break; }
+                    if (p != k) {
+                        for (int qq = t; qq < nbk; qq += T) {
+                            const double a = Tp[(size_t)k * CNB + qq];
+                            Tp[(size_t)k * CNB + qq] = Tp[(size_t)p * CNB + qq];
+                            Tp[(size_t)p * CNB + qq] = a;
+                        }
+                    }
+                    if (t == 0) ipiv[k] = p;
+                    gm_sync();
+                    const double pv = Tp[(size_t)k * CNB + q];
+                    for (int i = t; i < m; i += T) t1[i] = Tp[(size_t)i * CNB + q];
+                    for (int qq = t; qq < nbk; qq += T) prow[qq] = (qq == q ? 1.0 : Tp[(size_t)k * CNB + qq]) / pv;
+                    gm_sync();
+                    for_each_2d(m, nbk, [&](int i, int qq) {
+                        const double base = qq == q ? 0.0 : Tp[(size_t)i * CNB + qq];
+                        Tp[(size_t)i * CNB + qq] = i == k ? prow[qq] : base - t1[i] * prow[qq];
+                    });
+                    gm_sync();
+                }
+                if (!singular) {
+                    for_each_2d(m, nbk, [&](int i, int q) { M[(size_t)i * ldb + kb + q] = Tp[(size_t)i * CNB + q]; });
+                    gm_sync();
+                    for (int q = t; q < nbk; q += T) Tp[(size_t)(kb + q) * CNB + q] -= 1.0;
+                }
+                if (t == 0) mail[10] = singular;
+            }
+            grp_sync();  // panel done
+            singular = (int)mail[10];
+            if (singular) break;
+            {   // my column strip: row interchanges, then the pivot-row snapshot (column-wise, no barriers needed)
+                const int c0 = (int)(((long long)rank * m) / G), c1 = (int)(((long long)(rank + 1) * m) / G);
+                for (int j = c0 + t; j < c1; j += T) {
+                    if (j >= kb && j < kb + nbk) continue;
+                    for (int q = 0; q < nbk; ++q) {
+                        const int p = ipiv[kb + q];
+                        if (p != kb + q) {
+                            const double a = M[(size_t)(kb + q) * ldb + j];
+                            M[(size_t)(kb + q) * ldb + j] = M[(size_t)p * ldb + j];
+                            M[(size_t)p * ldb + j] = a;
+                        }
+                    }
+                    for (int q = 0; q < nbk; ++q) Rs[(size_t)q * ldb + j] = M[(size_t)(kb + q) * ldb + j];
+                }
+            }
+            grp_sync();  // snapshot done
+            {   // trailing update on the tensor cores
+                const int nrb = (m + 7) >> 3, ntile = (m + 7) >> 3;
+                const int arow = lane >> 2, acol = lane & 3;
+                for (int rb = rank; rb < nrb; rb += G) {
+                    const int i = rb * 8 + arow;
+                    double afr[CNB / 4];
+#pragma unroll
+                    for (int kk = 0; kk < CNB / 4; ++kk) {
+                        const int q = kk * 4 + acol;
+                        afr[kk] = (i < m && q < nbk) ? Tp[(size_t)i * CNB + q] : 0.0;
+                    }
+                    for (int jt = warp; jt < ntile; jt += nw) {
+                        const int j0 = jt * 8;
+                        if (j0 >= kb && j0 < kb + nbk) continue;  // the panel's own columns are already final
+                        const int jc = j0 + 2 * acol;
+                        double c0v = (i < m && jc < m) ? M[(size_t)i * ldb + jc] : 0.0;
+                        double c1v = (i < m && jc + 1 < m) ? M[(size_t)i * ldb + jc + 1] : 0.0;
+                        const int jb = j0 + arow;
+#pragma unroll
+                        for (int kk = 0; kk < CNB / 4; ++kk) {
+                            const int q = kk * 4 + acol;
+                            const double bfr = (q < nbk && jb < m) ? Rs[(size_t)q * ldb + jb] : 0.0;
+                            gm_dmma_8x8x4(c0v, c1v, afr[kk], bfr);
+                        }
+                        if (i < m && jc < m) M[(size_t)i * ldb + jc] = c0v;
+                        if (i < m && jc + 1 < m) M[(size_t)i * ldb + jc + 1] = c1v;
+                    }
+                }
+            }
+            grp_sync();  // update done
+        }
+        if (singular) {
+            if (cond1) *cond1 = INFINITY;
+            return 1;
+        }
+        // (PA)^-1 P : the column interchanges compose into one permutation (leader), applied row by row (all)
+        if (rank == 0) {
+            int* cp = inb;  // m ints of scratch (dead here: build_w refills it)
+            if (t == 0) {
+                for (int j = 0; j < m; ++j) cp[j] = j;
+                for (int k = m - 1; k >= 0; --k) {
+                    const int p = ipiv[k];
+                    const int a = cp[k];
+                    cp[k] = cp[p];
+                    cp[p] = a;
+                }
+            }
+        }
+        grp_sync();
+        for (int q = 0; q < nr; ++q) {
+            double* rowp = M + (size_t)(r0 + q) * ldb;
+            for (int j = t; j < m; j += T) s_prow[j] = rowp[j];
+            gm_sync();
+            for (int j = t; j < m; j += T) rowp[j] = s_prow[inb[j]];
+            gm_sync();
+        }
+        grp_sync();
+        coop_norms(M, r0, nr, inorm_inf, inorm_1);
+        if (cond1) *cond1 = anorm_1 * inorm_1;
+        anorm_w = fmax(anorm_1, anorm_inf);
+        const double cond_inf = anorm_inf * inorm_inf;
+        if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
+        return 0;
+    }
+
+    // ||M||_inf and ||M||_1 of the m x m matrix M (row stride ldb), computed by the whole group: row sums of my rows,
+    // column sums of my column strip, combined through the mailbox. One group barrier.
+    GM_DEV void coop_norms(const double* M, int r0, int nr, double& ninf, double& n1) {
+        const int t = gm_tid(), T = gm_nthreads();
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        double pinf = 0.0;
+        for (int q = warp; q < nr; q += nw) {
+            double sum = 0;
+            for (int j = lane; j < m; j += 32) sum += fabs(M[(size_t)(r0 + q) * ldb + j]);
+            for (int d = 16; d >= 1; d >>= 1) sum += gm_shfl_xor(sum, d);
+            pinf = (sum != sum) ? INFINITY : fmax(pinf, sum);
+        }
+        pinf = block_max(T, [&](int k) { return k == t ? pinf : 0.0; });
+        const int c0 = (int)(((long long)rank * m) / G), c1 = (int)(((long long)(rank + 1) * m) / G);
+        col_tile_reduce(M, ldb, m, c0, c1 - c0, s_r, [&](int, double v) { return fabs(v); });
+        const double p1 = block_max(c1 - c0, [&](int j) { return s_r[j]; });
+        if (t == 0) { rec_n(rank)[0] = pinf; rec_n(rank)[1] = p1; }
+        grp_sync();
+        ninf = block_max(G, [&](int g) { return rec_n(g)[0]; });
+        n1 = block_max(G, [&](int g) { return rec_n(g)[1]; });
+        grp_sync();
+    }
+
+    GM_DEV int invert_basis_coop(double* cond1) {
+        if (gm_tid() == 0) mail[0] = CMD_INVERT;
+        grp_sync();
+        return coop_invert_body(cond1);
+    }
+
+    // Helpers: execute what the leader posts until it says CMD_EXIT.
+    GM_DEV void coop_helper_loop() {
+        for (;;) {
+            grp_sync();
+            const int cmd = (int)mail[0];
+            if (cmd == CMD_EXIT) return;
+            if (cmd == CMD_MAIN) {
+                const double tol = mail[1];
+                const int phase = (int)mail[2];
+                bool fresh = mail[3] != 0.0;
+                int since = (int)mail[4];
+                piv1 = (int)mail[5]; piv2 = (int)mail[6]; cscale = mail[7]; nn = (int)mail[8]; ncols = (int)mail[9];
+                int e = 0;
+                coop_loop(tol, phase, fresh, since, e);
+            } else if (cmd == CMD_INVERT) {
+                coop_invert_body(nullptr);
+            }
+        }
+    }
+    GM_DEV void coop_post_exit() {
+        if (gm_tid() == 0) mail[0] = CMD_EXIT;
+        grp_sync();
     }
 
     // ---- findInitialBasic, simplex.go:492-607. On GM_OK: basic, W (n columns), Bi, xb, y, cb, cn set ---
@@ -1769,7 +2423,7 @@ struct SolverT {
             gm_sync();
             for (int p = t; p < m; p += T) inb[basic[p]] = 1;
             gm_sync();
-            bool done = false;
+            bool done = false, weak = false;
             for (int v = 0; v < n && !done; ++v) {
                 if (inb[v]) continue;
                 nrepair++;
@@ -1778,7 +2432,10 @@ struct SolverT {
                 bi_mul(al, t1);
                 const double amax = block_max(m, [&](int q) { return fabs(al[q]); });
                 const double ap = al[added];
-                if (!(fabs(ap) > 1e-9 * fmax(1.0, amax))) continue;  // swapped basis (near-)singular
+                // initializeFromBasic on the swapped basis (:594-600): LU.Solve fails iff the factor is exactly
+                // singular or cond_inf > 1e16 (lu.go:301,321); then the positivity test :459-468
+                if (!(swapped_cond(added, true) <= GM_CONDITION_TOL)) continue;
+                weak = !(fabs(ap) > 1e-9 * fmax(1.0, amax));
                 const double theta = xb[added] / ap;
                 const int bad = block_min_int(m, [&](int i) {
                     const double nx = (i == added) ? theta : xb[i] - al[i] * theta;
@@ -1793,6 +2450,14 @@ struct SolverT {
                 fresh = false;
             }
             if (!done) return GM_ERR_INFEASIBLE;
+            if (weak) {  // the accepted pivot element is noise against its column: do not keep the product form
+                build_w(n, false);
+                double c1;
+                if (invert_basis(&c1)) return GM_ERR_PHASE1_WRAPPED + GM_ERR_CONDITION;
+                recompute_xb_y();
+                fresh = true;
+                return GM_OK;
+            }
         }
         build_w(n, false);  // Phase II lists: basis positions kept, non-basic ascending again (:174-197)
         bi_mul_t(y, cb);
@@ -1906,7 +2571,8 @@ struct SolverT {
         }
         if (P.basis) {
             long long* bo = P.basis + (size_t)lp * m;
-            for (int p = t; p < m; p += T) bo[p] = have_basis ? (long long)basic[p] : -1;
+            const bool keep = have_basis && !(WARM && P.bi_out && status != GM_OK);
+            for (int p = t; p < m; p += T) bo[p] = keep ? (long long)basic[p] : -1;
         }
         if (WARM && P.bi_out && have_basis && status == GM_OK) {
             double* out = P.bi_out + (size_t)lp * m * m;
@@ -1936,6 +2602,7 @@ struct SolverT {
     // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
     GM_DEV void bind_workspace(const BatchParams& P, double* wbase, double* bibase, double* small,
                                double* ring_base = nullptr, unsigned long long* bars = nullptr) {
+        G = 1; rank = 0; gbar = nullptr; epoch = 0; mail = nullptr;
         ring = ring_base; ring_bar = bars; ring_ns = P.ring_stages; ring_stage_doubles = P.ring_stage_bytes / 8;
         ring_uses = 0;
         stream_min_m = P.stream_min_m;
@@ -1963,6 +2630,9 @@ struct SolverT {
         bsign = P.bsign ? P.bsign + (size_t)lp * L : nullptr;
         brhs = P.brhs ? P.brhs + (size_t)lp * L : nullptr;
         ncols = n; nn = n - m;
+        trace_out = (WARM && P.trace && lp == P.trace_lp) ? P.trace : nullptr;
+        trace_cap = P.trace_cap;
+        cur_phase = 2; cur_bland = 0;
     }
 };
 
@@ -1989,6 +2659,47 @@ GM_DEV void cta_main(const BatchParams& P, double* wbase, double* bibase, double
         s.bind_lp(P, lp);
         s.solve(P, lp);
     }
+}
+
+// Cooperative tier: CTA b is rank b % G of group b / G. The leader pulls LPs from the queue and solves them with the
+// group's help; the helpers serve until the leader posts CMD_EXIT. `smem` = this CTA's dynamic shared memory.
+GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
+    SolverT<false, true, true> s;
+    const int G = P.coop_G, T = gm_nthreads();
+    const int grp = gm_block_id() / G;
+    const int m = P.m0 + P.L, n = P.n0 + P.L;
+    const WsLayout w = ws_layout(m, n, T, false, true);
+    const CoopLayout c = coop_layout(m, n, T, G);
+    double* base = P.work + (size_t)grp * P.work_stride;
+    s.bind_workspace(P, base + w.W, base + w.Bi, base + w.big_doubles, nullptr, nullptr);
+    s.G = G;
+    s.rank = gm_block_id() % G;
+    s.gbar = P.coop_bar + grp;
+    s.epoch = 0;
+    s.mail = base + c.mail;
+    s.Bi1 = base + c.Bi1; s.Tp = base + c.Tp; s.Rs = base + c.Rs;
+    s.s_y = smem + c.s_y; s.s_prow = smem + c.s_prow; s.s_ae = smem + c.s_ae; s.s_xb = smem + c.s_xb;
+    s.s_al = smem + c.s_al; s.s_f = smem + c.s_f; s.s_r = smem + c.s_r; s.s_part = smem + c.s_part;
+    s.red = smem + c.s_red;                                   // block reductions go through shared memory
+    s.s_bit = reinterpret_cast<int*>(smem + c.s_bit);
+    s.redi = reinterpret_cast<int*>(smem + c.s_redi);
+    if (s.rank != 0) {
+        s.piv1 = s.piv2 = s.ninv = 0;
+        s.trace_out = nullptr;
+        s.coop_helper_loop();
+        return;
+    }
+    for (;;) {
+        if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
+        gm_sync();
+        const int item = *slot;
+        gm_sync();
+        if (item >= P.count) break;
+        const int lp = P.lp_list ? P.lp_list[item] : item;
+        s.bind_lp(P, lp);
+        s.solve(P, lp);
+    }
+    s.coop_post_exit();
 }
 
 }  // namespace gm

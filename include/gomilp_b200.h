@@ -28,7 +28,9 @@ extern "C" {
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int gm_device_count(void);       /* number of CUDA devices visible, 0 if none */
-int gm_init(int device);         /* bind the calling process to `device`; GM_OK / GM_ERR_NO_DEVICE / GM_ERR_CUDA */
+int gm_init(int device);         /* bind the CALLING THREAD to `device` (one engine context per device; threads that
+                                    never call gm_init use the first device initialised); GM_OK / GM_ERR_NO_DEVICE /
+                                    GM_ERR_CUDA. Roots remember their device: a wave runs where its root lives. */
 int gm_shutdown(void);           /* release roots, streams and cached workspaces */
 const char* gm_last_error(void); /* message of the last GM_ERR_CUDA on the calling thread */
 
@@ -42,7 +44,8 @@ typedef struct gm_timing {
     int64_t smem_bytes; /* dynamic shared memory per CTA (0: HBM-resident tier) */
     int32_t tier;       /* 1 = basis inverse in registers + W in shared memory (m <= 64), 2 = all in shared memory,
                            3 = inverse + vectors in shared memory, W in HBM, 4 = W and inverse in HBM behind a TMA
-                           staging ring, vectors in shared memory, 5 = all in HBM */
+                           staging ring, vectors in shared memory, 5 = all in HBM, 6 = cooperative: several CTAs
+                           (grid / LPs) share one LP, state in HBM / L2 (fewer LPs than SMs) */
     int32_t grid, block;
 } gm_timing;
 int gm_last_timing(gm_timing* out);
@@ -52,9 +55,18 @@ typedef struct gm_options {
     int32_t max_pivots;      /* safety cap per LP; the reference has none. default 50*(m+n)+1000 */
     int32_t refactor_period; /* pivots between rebuilds of the basis inverse. default 100 */
     int32_t force_tier;      /* 0 auto, else the gm_timing.tier to force (GM_ERR_TOO_LARGE if it does not fit) */
-    int32_t reserved;        /* 1: tier 3 without the TMA staging ring (plain loads), for A/B measurements */
+    int32_t reserved;        /* 1: tier 4 without the TMA staging ring (plain loads), for A/B measurements */
+    int32_t coop_group;      /* tier 6: CTAs per LP. default min(SMs / LPs in the launch, m / 2) */
+    int32_t reserved2;
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
+
+/* Pivot trace (parity evidence, BASELINE.json "identical ... branching sequences where pivots tie-break
+ * identically"): arm before a host-buffer compute call on this thread; LP `lp_index` of that call records its first
+ * `cap` pivots as int32 rows (phase 1|2, entering variable, leaving variable, chosen by replaceBland 0|1) - the
+ * quantities simplex.go:233-293 decides per iteration. gm_trace_fetch copies up to cap rows (-1 = unused). */
+int gm_trace_arm(int64_t lp_index, int64_t cap);
+int64_t gm_trace_fetch(int32_t* rows, int64_t cap);
 
 /* ---- (1) one LP: lp.Simplex, simplex.go:88 -----------------------------------------------------
  * min c'x s.t. Ax = b, x >= 0. A row-major m x n with row stride lda (mat.Dense layout).
@@ -130,6 +142,25 @@ int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const double* A, c
                   const double* G, const double* h, const uint8_t* integrality, int32_t heuristic, int32_t mode,
                   int64_t node_limit, double time_limit_s, double* x, gm_milp_result* result,
                   gm_decision_cb on_decision, gm_wave_cb on_wave, void* user);
+
+/* ---- (3b) the same search with the decisions made on the device, optionally sharded over several GPUs ------------
+ * gm_milp_solve_device = gm_milp_solve(..., mode | GM_BNB_DEVICE_SCAN, ...): tree.go's FIFO queue becomes a per-GPU
+ * wavefront, checkSolution (tree.go:207-263) an exclusive prefix-min scan over 32-byte node records, branching.go
+ * reads x from device buffers. With a communicator (below) every rank calls it with IDENTICAL arguments: rank r solves
+ * the r-th contiguous FIFO block of every wave, the node records are exchanged with one ncclAllGather per wave over
+ * NVLink, and every rank returns the same result (the incumbent's x is broadcast from the rank that found it).
+ * time_limit_s is honoured only without a communicator (ranks must agree on where to stop: use node_limit). */
+int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const double* A, const double* b, int64_t nineq,
+                         const double* G, const double* h, const uint8_t* integrality, int32_t heuristic, int32_t mode,
+                         int64_t node_limit, double time_limit_s, double* x, gm_milp_result* result,
+                         gm_decision_cb on_decision, gm_wave_cb on_wave, void* user);
+
+/* Communicator of the calling thread (one rank per GPU; NCCL is loaded at run time, libnccl.so.2).
+ * Rank 0 creates the 128-byte id and hands it to the other ranks by any means (the Go side: a channel or a file;
+ * the tests: torch.distributed / multiprocessing). gm_comm_init binds the rank to the thread's current device. */
+int gm_comm_unique_id(void* id128);
+int gm_comm_init(int32_t rank, int32_t world, const void* id128);
+int gm_comm_destroy(void);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,10 @@ typedef enum gm_bnb_mode { GM_BNB_COMPAT = 0, GM_BNB_FIXED = 1 } gm_bnb_mode;
 /* OR-ed into `mode`: children start from their parent's optimal basis (gm_solve_wave_warm) instead of from
  * scratch. Same optima where they are unique, far fewer pivots; not a pivot-for-pivot replay of the reference. */
 #define GM_BNB_WARM_START 4
+/* OR-ed into `mode`: checkSolution / feasibleForIP / branch run on the device (node_check + wave_scan kernels) so that
+ * x never leaves the GPU, and the wave is sharded over the ranks of gm_comm_init when a communicator is set. Same
+ * decisions, ids and node counts as the host replay (gm_milp_solve without the flag). Children are solved cold. */
+#define GM_BNB_DEVICE_SCAN 8
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,8 @@ def lib():
     L.orc_solve_vec.restype = C.c_int
     L.orc_solve_vec.argtypes = [_f64p, C.c_int64, C.c_int, _f64p, _f64p, C.POINTER(C.c_double)]
     L.orc_num_hw_threads.restype = C.c_int
+    L.orc_find_linearly_independent.restype = C.c_int
+    L.orc_find_linearly_independent.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int64, _i64p]
     _lib = L
     return L
 
@@ -230,6 +232,15 @@ def solve_vec(a, b, transpose: bool = False):
     cond = C.c_double(0.0)
     rc = lib().orc_solve_vec(a, n, int(transpose), _f64(b), x, C.byref(cond))
     return rc, x, cond.value
+
+
+def initial_basis(A):
+    """findLinearlyIndependent (simplex.go:611-637): accepted column indices in acceptance order, None if < m."""
+    A = _f64(A)
+    m, n = A.shape
+    idx = np.zeros(m, dtype=np.int64)
+    k = lib().orc_find_linearly_independent(A, n, m, n, idx)
+    return idx if k == m else None
 
 
 def num_hw_threads() -> int:

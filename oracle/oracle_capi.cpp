@@ -162,5 +162,13 @@ int orc_solve_vec(const double* a, int64_t n, int transpose, const double* b, do
     return (int)solve_vec(a, (int)n, (int)n, transpose != 0, b, x, cond);
 }
 int orc_num_hw_threads() { return (int)std::thread::hardware_concurrency(); }
+// findLinearlyIndependent (simplex.go:611-637) alone: the column indices it accepts, in acceptance order.
+// Returns how many were accepted (< m: lp.ErrSingular at simplex.go:495-498).
+int orc_find_linearly_independent(const double* A, int64_t lda, int64_t m, int64_t n, int64_t* idxs) {
+    SimplexStats st;
+    ivec r = detail::find_linearly_independent(A, (int)lda, (int)m, (int)n, st);
+    for (size_t i = 0; i < r.size(); ++i) idxs[i] = r[i];
+    return (int)r.size();
+}
 
 }  // extern "C"

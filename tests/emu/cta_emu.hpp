@@ -27,7 +27,8 @@ namespace emu {
 enum Wait { RUN = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
 
 struct Cta {
-    int T = 0;
+    int T = 0;        // threads per CTA
+    int NB = 1;       // CTAs emulated together (a cooperative launch); fiber f = block * T + thread
     int cur = 0;
     std::vector<ucontext_t> ctx;
     std::vector<std::vector<char>> stacks;
@@ -61,9 +62,18 @@ inline void trampoline() {
 
 // Runs body() on T fibers to completion. Throws on barrier divergence (some threads exit or wait on a
 // different barrier kind while others wait forever).
+inline void run_grid(int nblocks, int T, std::function<void()> body, bool shuffle_order = false,
+                     size_t stack_bytes = 256 * 1024);
 inline void run_cta(int T, std::function<void()> body, bool shuffle_order = false, size_t stack_bytes = 256 * 1024) {
+    run_grid(1, T, std::move(body), shuffle_order, stack_bytes);
+}
+// `nblocks` CTAs of T threads each, all resident at once (what a cooperative launch guarantees). Block barriers
+// release per CTA; CTAs talk to each other only through memory (atomics + spin loops that call gm_spin_pause()).
+inline void run_grid(int nblocks, int Tper, std::function<void()> body, bool shuffle_order, size_t stack_bytes) {
     Cta c;
-    c.T = T;
+    c.T = Tper;
+    c.NB = nblocks;
+    const int T = Tper * nblocks;
     c.body = std::move(body);
     c.ctx.resize(T);
     c.stacks.resize(T);
@@ -110,18 +120,23 @@ inline void run_cta(int T, std::function<void()> body, bool shuffle_order = fals
                 progressed = true;
             }
         }
-        int nblock = 0, ndone = 0, nrun = 0;
+        int ndone = 0, nrun = 0;
+        bool released = false;
+        for (int b0 = 0; b0 < T; b0 += Tper) {  // block barriers release per CTA
+            int nblock = 0;
+            for (int t = b0; t < b0 + Tper; ++t) nblock += c.state[t] == WAIT_BLOCK;
+            if (nblock == Tper) {
+                for (int t = b0; t < b0 + Tper; ++t) c.state[t] = RUN;
+                c.barriers++;
+                released = true;
+            }
+        }
         for (int t = 0; t < T; ++t) {
-            nblock += c.state[t] == WAIT_BLOCK;
             ndone += c.state[t] == DONE;
             nrun += c.state[t] == RUN;
         }
         if (ndone == T) break;
-        if (nblock == T) {
-            for (int t = 0; t < T; ++t) c.state[t] = RUN;
-            c.barriers++;
-            continue;
-        }
+        if (released) continue;
         if (nrun == 0 && !progressed) {
             current() = prev;
             throw std::runtime_error("cta_emu: barrier divergence / deadlock");
@@ -160,7 +175,7 @@ inline V shfl_generic(V v, int src_lane_abs_valid, int src) {
 
 #define GM_DEV inline
 #define GM_DEV_NOINLINE inline
-inline int gm_tid() { return emu::current()->cur; }
+inline int gm_tid() { return emu::current()->cur % emu::current()->T; }
 inline int gm_nthreads() { return emu::current()->T; }
 inline void gm_sync() { emu::yield_as(emu::WAIT_BLOCK); }
 template <class V>
@@ -168,14 +183,14 @@ inline V gm_shfl_down_t(V v, int d) {
     emu::Cta* c = emu::current();
     int lane = c->cur & 31;
     int src = c->cur + d;
-    bool ok = (lane + d) < 32 && src < c->T;
+    bool ok = (lane + d) < 32 && src < (c->T * c->NB);
     return emu::shfl_generic(v, ok, src);
 }
 template <class V>
 inline V gm_shfl_xor_t(V v, int d) {
     emu::Cta* c = emu::current();
     int src = (c->cur & ~31) | ((c->cur & 31) ^ d);
-    bool ok = src < c->T;
+    bool ok = src < (c->T * c->NB);
     return emu::shfl_generic(v, ok, src);
 }
 inline double gm_shfl_down(double v, int d) { return gm_shfl_down_t(v, d); }
@@ -185,18 +200,18 @@ inline int gm_shfl_xor(int v, int d) { return gm_shfl_xor_t(v, d); }
 inline double gm_shfl_idx(double v, int src_lane) {
     emu::Cta* c = emu::current();
     int src = (c->cur & ~31) | (src_lane & 31);
-    return emu::shfl_generic(v, src < c->T, src);
+    return emu::shfl_generic(v, src < (c->T * c->NB), src);
 }
 inline int gm_shfl_idx(int v, int src_lane) {
     emu::Cta* c = emu::current();
     int src = (c->cur & ~31) | (src_lane & 31);
-    return emu::shfl_generic(v, src < c->T, src);
+    return emu::shfl_generic(v, src < (c->T * c->NB), src);
 }
 inline unsigned gm_ballot(int pred) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = pred ? 1 : 0;
     emu::yield_as(emu::WAIT_WARP);
-    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    int w0 = c->cur & ~31, w1 = std::min((c->T * c->NB), w0 + 32);
     unsigned r = 0;
     for (int t = w0; t < w1; ++t) r |= (unsigned)c->vote[t] << (t - w0);
     emu::yield_as(emu::WAIT_WARP);
@@ -206,7 +221,7 @@ inline int gm_warp_min_int(int v) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = v;
     emu::yield_as(emu::WAIT_WARP);
-    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32), r = INT_MAX;
+    int w0 = c->cur & ~31, w1 = std::min((c->T * c->NB), w0 + 32), r = INT_MAX;
     for (int t = w0; t < w1; ++t) r = std::min(r, c->vote[t]);
     emu::yield_as(emu::WAIT_WARP);
     return r;
@@ -215,7 +230,7 @@ inline unsigned gm_warp_min_u32(unsigned v) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = (int)v;
     emu::yield_as(emu::WAIT_WARP);
-    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    int w0 = c->cur & ~31, w1 = std::min((c->T * c->NB), w0 + 32);
     unsigned r = 0xffffffffu;
     for (int t = w0; t < w1; ++t) r = std::min(r, (unsigned)c->vote[t]);
     emu::yield_as(emu::WAIT_WARP);
@@ -225,7 +240,7 @@ inline unsigned gm_warp_max_u32(unsigned v) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = (int)v;
     emu::yield_as(emu::WAIT_WARP);
-    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32);
+    int w0 = c->cur & ~31, w1 = std::min((c->T * c->NB), w0 + 32);
     unsigned r = 0;
     for (int t = w0; t < w1; ++t) r = std::max(r, (unsigned)c->vote[t]);
     emu::yield_as(emu::WAIT_WARP);
@@ -247,7 +262,7 @@ inline int gm_any(int pred) {
     emu::Cta* c = emu::current();
     c->vote[c->cur] = pred ? 1 : 0;
     emu::yield_as(emu::WAIT_WARP);
-    int w0 = c->cur & ~31, w1 = std::min(c->T, w0 + 32), r = 0;
+    int w0 = c->cur & ~31, w1 = std::min((c->T * c->NB), w0 + 32), r = 0;
     for (int t = w0; t < w1; ++t) r |= c->vote[t];
     emu::yield_as(emu::WAIT_WARP);
     return r;
@@ -258,6 +273,39 @@ inline int gm_atomic_add(int* p, int v) {
     return o;
 }
 inline double gm_ldg(const double* p) { return *p; }
+
+// ---- multi-CTA groups ------------------------------------------------------------------------------------------
+inline int gm_block_id() { return emu::current()->cur / emu::current()->T; }
+inline void gm_threadfence() {}
+inline void gm_spin_pause() { emu::yield_as(emu::RUN); }
+inline void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+inline unsigned long long gm_ld_acquire_u64(const unsigned long long* p) { return *(volatile const unsigned long long*)p; }
+// D(8x8) = A(8x4) * B(4x8) + C with the m8n8k4 fragment layout of mma.sync (see cta_rt.cuh)
+inline void gm_dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    emu::Cta* c = emu::current();
+    const int lane = c->cur & 31, w0 = c->cur & ~31;
+    uint64_t ab, bb;
+    std::memcpy(&ab, &a, 8);
+    std::memcpy(&bb, &b, 8);
+    c->slot[c->cur] = ab;
+    emu::yield_as(emu::WAIT_WARP);
+    double arow[4];
+    for (int k = 0; k < 4; ++k) std::memcpy(&arow[k], &c->slot[w0 + (lane >> 2) * 4 + k], 8);  // A[row][k]
+    emu::yield_as(emu::WAIT_WARP);
+    c->slot[c->cur] = bb;
+    emu::yield_as(emu::WAIT_WARP);
+    for (int u = 0; u < 2; ++u) {
+        const int col = 2 * (lane & 3) + u;
+        double acc = u == 0 ? c0 : c1;
+        for (int k = 0; k < 4; ++k) {
+            double bv;
+            std::memcpy(&bv, &c->slot[w0 + col * 4 + k], 8);  // B[k][col] is held by lane col*4 + k
+            acc += arow[k] * bv;
+        }
+        (u == 0 ? c0 : c1) = acc;
+    }
+    emu::yield_as(emu::WAIT_WARP);
+}
 
 // ---- TMA bulk copy + mbarrier stand-ins: the copy happens at issue time, the barrier counts bytes ----------
 // An emulated mbarrier word: low 32 bits = bytes still expected in the current phase (two's complement while

@@ -77,6 +77,53 @@ int emu_simplex_batch_ex(int count, const double* c, const double* A, const doub
     return 0;
 }
 
+
+// The cooperative tier (simplex_cta.cuh, COOP): `groups` groups of G emulated CTAs of T threads each, all resident at
+// once like a cooperative launch. trace (optional): int[trace_cap][4] pivot records of LP trace_lp.
+int emu_coop_batch(int count, const double* c, const double* A, const double* b, long long c_stride,
+                   long long A_stride, long long b_stride, int lda, int m0, int n0, int L, const int* bvar,
+                   const double* bsign, const double* brhs, const long long* initial_basic, double tol, int max_pivots,
+                   int refactor_period, int* status, double* optF, double* x, long long x_stride, int x_len,
+                   long long* basis, int* stats, int T, int G, int groups, int shuffle_order, int* trace, int trace_cap,
+                   int trace_lp) {
+    gm::BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.c = c; P.A = A; P.b = b;
+    P.c_stride = c_stride; P.A_stride = A_stride; P.b_stride = b_stride;
+    P.lda = lda; P.m0 = m0; P.n0 = n0; P.L = L;
+    P.bvar = bvar; P.bsign = bsign; P.brhs = brhs;
+    P.initial_basic = initial_basic;
+    P.tol = tol; P.count = count; P.max_pivots = max_pivots; P.refactor_period = refactor_period;
+    P.status = status; P.optF = optF; P.x = x; P.x_stride = x_stride; P.x_len = x_len;
+    P.basis = basis; P.stats = stats;
+    P.trace = trace; P.trace_cap = trace_cap; P.trace_lp = trace_lp;
+    int queue = 0;
+    P.queue = &queue;
+    P.hbm_layout = 1;
+    P.tier = 6;
+    P.coop_G = G;
+    if (T % 32 != 0 || G < 1 || groups < 1) return -2;
+    const gm::CoopLayout cl = gm::coop_layout(m0 + L, n0 + L, T, G);
+    std::vector<double> work((size_t)groups * cl.group_doubles + 16, 0.0);
+    std::vector<unsigned long long> bars(groups, 0ull);
+    P.work = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(work.data()) + 31) & ~uintptr_t(31));
+    P.work_stride = (long long)cl.group_doubles;
+    P.coop_bar = bars.data();
+    const int nblocks = G * groups;
+    std::vector<std::vector<double>> smem(nblocks, std::vector<double>(cl.smem_bytes / 8 + 8, 0.0));
+    std::vector<int> slots(nblocks, 0);
+    try {
+        emu::run_grid(nblocks, T, [&]() {
+            const int b2 = gm_block_id();
+            gm::coop_cta_main(P, smem[b2].data(), &slots[b2]);
+        }, shuffle_order != 0);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+
 }  // extern "C"
 
 // ---- emulator-backed stand-ins for the wave entry points, so that the product's B&B host
@@ -161,6 +208,12 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
     r.prev_nodes = nodes;
     r.prev_m = (int)m;
     return rc == 0 ? GM_OK : GM_ERR_CUDA;
+}
+// the device-side scan (bnb_device.cu) is CUDA only: not available in the emulator build
+int gm_milp_solve_device(int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*,
+                         const double*, const uint8_t*, int32_t, int32_t, int64_t, double, double*, gm_milp_result*,
+                         gm_decision_cb, gm_wave_cb, void*) {
+    return GM_ERR_NO_DEVICE;
 }
 }  // extern "C"
 

@@ -87,6 +87,42 @@ def simplex_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, initial_ba
     return {"status": status, "optF": optF, "x": x, "basis": basis, "stats": stats}
 
 
+def coop_batch(c, A, b, tol=0.0, bvar=None, bsign=None, brhs=None, T=64, G=3, groups=1, max_pivots=0,
+               refactor_period=0, shared_root=False, shuffle_order=False, trace_cap=0, trace_lp=0):
+    """Batch of LPs through the emulated COOPERATIVE tier: `groups` groups of G CTAs (T threads each) share the work."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    if shared_root:
+        m0, n0 = A.shape
+        count, L = bvar.shape
+        cs = As = bs = 0
+        bvar = np.ascontiguousarray(bvar, dtype=np.int32)
+        bsign = np.ascontiguousarray(bsign, dtype=np.float64)
+        brhs = np.ascontiguousarray(brhs, dtype=np.float64)
+    else:
+        count, m0, n0 = A.shape
+        L = 0
+        cs, As, bs = n0, m0 * n0, m0
+    m = m0 + L
+    x_len = n0 if shared_root else n0 + L
+    status = np.zeros(count, dtype=np.int32)
+    optF = np.zeros(count)
+    x = np.zeros((count, x_len))
+    basis = np.zeros((count, m), dtype=np.int64)
+    stats = np.zeros((count, 8), dtype=np.int32)
+    trace = np.full((max(trace_cap, 1), 4), -1, dtype=np.int32)
+    rc = lib().emu_coop_batch(C.c_int(count), _p(c), _p(A), _p(b), C.c_longlong(cs), C.c_longlong(As), C.c_longlong(bs),
+                              C.c_int(n0), C.c_int(m0), C.c_int(n0), C.c_int(L), _p(bvar), _p(bsign), _p(brhs), None,
+                              C.c_double(tol), C.c_int(max_pivots), C.c_int(refactor_period), _p(status), _p(optF),
+                              _p(x), C.c_longlong(x_len), C.c_int(x_len), _p(basis), _p(stats), C.c_int(T), C.c_int(G),
+                              C.c_int(groups), C.c_int(int(shuffle_order)), _p(trace) if trace_cap else None,
+                              C.c_int(trace_cap), C.c_int(trace_lp))
+    if rc != 0:
+        raise RuntimeError("CTA emulator: barrier divergence" if rc == -1 else "CTA emulator: bad request")
+    return {"status": status, "optF": optF, "x": x, "basis": basis, "stats": stats, "trace": trace}
+
+
 class _MilpRes(C.Structure):
     _fields_ = [("status", C.c_int32), ("lp_status", C.c_int32), ("z", C.c_double), ("x_len", C.c_int64),
                 ("nodes", C.c_int64), ("waves", C.c_int64), ("pivots", C.c_int64), ("device_ms", C.c_double)]

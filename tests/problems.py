@@ -89,3 +89,42 @@ def standard_form(p: dict):
         b0[meq:] = p["h"]
     c0 = np.concatenate([c, np.zeros(nineq)])
     return c0, A0, b0
+
+
+def c5_general_integer(n: int):
+    """Config C5: general-integer MILP, m_ineq = n/2 dense rows G ~ U(0,1), h = G u / 2, bounds
+    0 <= x <= u = 10 materialised as rows like api.go:245-272 does, c ~ -U(0,1) (min), seed 100 + n."""
+    rng = np.random.default_rng(100 + n)
+    mi = n // 2
+    Gd = rng.random((mi, n))
+    u = 10.0
+    G = np.vstack([Gd, np.eye(n)])
+    h = np.concatenate([0.5 * Gd @ np.full(n, u), np.full(n, u)])
+    return dict(c=-rng.random(n), A=None, b=None, G=G, h=h, integrality=np.ones(n, dtype=np.uint8))
+
+
+def node_lp(c0, A0, b0, bvar, bsign, brhs):
+    """The explicit LP of one B&B node: [A0 0; G I] x = [b0; h] with one row per bnbConstraint
+    (combineInequalities + convertToEqualities, subproblem.go:55-139)."""
+    m0, n0 = A0.shape
+    L = len(bvar)
+    A = np.zeros((m0 + L, n0 + L))
+    A[:m0, :n0] = A0
+    for l in range(L):
+        A[m0 + l, int(bvar[l])] = bsign[l]
+        A[m0 + l, n0 + l] = 1.0
+    return np.concatenate([c0, np.zeros(L)]), A, np.concatenate([b0, np.asarray(brhs, dtype=np.float64)])
+
+
+def most_infeasible(x, integ) -> int:
+    """FIXED-mode most-infeasible branching point (bnb_host.cpp fixed_point): the integer-flagged variable whose
+    fractional part is closest to 1/2, first one on ties; -1 when x is integer feasible (exact x == trunc(x))."""
+    best, bestv = -1, -1.0
+    for i in range(len(x)):
+        if not integ[i] or x[i] == np.trunc(x[i]):
+            continue
+        f = x[i] - np.floor(x[i])
+        score = 0.5 - abs(0.5 - f)
+        if score > bestv:
+            best, bestv = i, score
+    return best
