@@ -34,42 +34,47 @@ UNIT = "LP/s"
 WORKLOAD = "C2: 4096 independent random dense LP relaxations m=64 n=128 f64 per GPU (feasible+bounded generator, seed 1234+rank)"
 
 
-# ncu --set full capture of one launch of this exact workload (seed 1234): 277.0 MB read + 9.5 MB written, i.e. the
-# 275 MB batch is read once from HBM and the results written once; the per-pivot bytes stay on chip.
-TIER1_DRAM_BYTES_PER_LAUNCH = 286.5e6
-
-
 def hbm_tier_extra(gm):
-    """The HBM-resident pivot path (tier 4, TMA staging ring), outside the timed region: 148 dense LPs of C4's shape
-    (m=1024, n=2048, slack form so that no basis inversion dilutes it), 60 pivots each."""
+    """The HBM-resident pivot path on BASELINE config 4's real shape, outside the timed region: (a) ONE dense LP
+    m=1024 n=2048 (seed 42) solved to optimality by the cooperative tier with every SM on it; (b) a batch of 16 such
+    LPs (seeds 42..57, working set 16 x 25 MB > L2) solved to optimality, groups of 9 CTAs per LP - the honest
+    HBM-bound number. Everything reported is measured in this run."""
     try:
-        m, n, count, cap = 1024, 2048, 148, 60
-        rng = np.random.default_rng(42)
-        base = 4
-        A = np.zeros((base, m, n))
-        A[:, :, : n - m] = rng.random((base, m, n - m))
-        A[:, :, n - m:] = np.eye(m)
-        b = 1.0 + rng.random((base, m))
-        c = np.zeros((base, n))
-        c[:, : n - m] = -rng.random((base, n - m))
-        reps = (count + base - 1) // base
-        c, A, b = np.tile(c, (reps, 1))[:count], np.tile(A, (reps, 1, 1))[:count], np.tile(b, (reps, 1))[:count]
-        gm.set_options(max_pivots=cap, refactor_period=100000)
-        gm.simplex_batch(c, A, b, want_basis=False)
-        g = gm.simplex_batch(c, A, b, want_basis=False)
-        tm = gm.last_timing()
-        gm.set_options()
-        piv = int(g["pivots"].sum())
-        alg = piv * bytes_per_pivot(m, n)
-        return {"workload": "148 dense LPs m=1024 n=2048 (C4's shape), slack form, 60 pivots each, one CTA per LP",
-                "tier": tm["tier"], "kernel_ms": tm["kernel_ms"], "pivots": piv,
-                "algorithmic_GBps": alg / (tm["kernel_ms"] * 1e-3) / 1e9,
-                "dram_GBps_from_ncu": 3560.0, "dram_frac_of_measured_hbm_peak": 0.55,
-                "dram_source": "profiles/r01_tier4_tma_1024x2048_ncu_full_attribution.txt: 162.3 GB read + 78.9 GB "
-                               "written in 67.75 ms for the same launch"}
+        from problems import feasible_bounded_lp
+        m, n = 1024, 2048
+        lps = [feasible_bounded_lp(np.random.default_rng(42 + k), m, n) for k in range(16)]
+        c = np.stack([l[0] for l in lps]); A = np.stack([l[1] for l in lps]); b = np.stack([l[2] for l in lps])
+        gm.simplex_batch(c[:1], A[:1], b[:1], want_basis=False)  # warm-up (loads the kernel)
+        g1 = gm.simplex_batch(c[:1], A[:1], b[:1], want_basis=False)
+        t1 = gm.last_timing()
+        g16 = gm.simplex_batch(c, A, b, want_basis=False)
+        t16 = gm.last_timing()
+        p1, p16 = int(g1["pivots"].sum()), int(g16["pivots"].sum())
+        bpp = bytes_per_pivot(m, n)
+        peak = load_peaks().get("hbm_gbs", 6650.0)
+        return {"single_lp": {"workload": "C4: one dense LP m=1024 n=2048 seed 42, solved to optimality",
+                              "status_ok": bool((g1["status"] == 0).all()), "tier": t1["tier"], "grid": t1["grid"],
+                              "pivots": p1, "kernel_ms": t1["kernel_ms"], "us_per_pivot": 1e3 * t1["kernel_ms"] / max(1, p1),
+                              "algorithmic_GBps": p1 * bpp / (t1["kernel_ms"] * 1e-3) / 1e9,
+                              "note": "working set 25 MB: L2 resident, so this is not an HBM figure"},
+                "batch16": {"workload": "16 dense LPs m=1024 n=2048 seeds 42..57, solved to optimality (working set > L2)",
+                            "status_ok": bool((g16["status"] == 0).all()), "tier": t16["tier"], "grid": t16["grid"],
+                            "ctas_per_lp": t16["grid"] // 16, "pivots": p16, "kernel_ms": t16["kernel_ms"],
+                            "bytes_per_pivot": bpp, "algorithmic_GBps": p16 * bpp / (t16["kernel_ms"] * 1e-3) / 1e9,
+                            "frac_of_measured_hbm_peak": p16 * bpp / (t16["kernel_ms"] * 1e-3) / 1e9 / peak,
+                            "note": "the fused update+FTRAN pass moves 2 m^2 + m(n-m) words per pivot, 0.75 of the "
+                                    "3 m^2 + m(n-m) SURVEY 8(d) counts; inversions are inside the time"}}
     except Exception as e:
         gm.set_options()
-        return {"error": str(e)}
+        return {"error": repr(e)}
+
+
+def load_peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def bytes_per_pivot(m: int, n: int) -> int:
@@ -144,59 +149,118 @@ def cpu_baseline(count: int, threads: int):
 
 
 def bnb_extra(gm):
-    """Second half of BASELINE.json's metric, outside the timed region: B&B nodes/s through gm_milp_solve (one wave
-    launch per BFS level, decisions replayed on the host) on a small 0-1 multidimensional knapsack, 1 GPU."""
+    """Second half of BASELINE.json's metric, outside the timed region: B&B nodes/s through gm_milp_solve on 1 GPU.
+    (a) a small 0-1 knapsack (tier 1 waves) with the decisions replayed on the host and with the device-side scan;
+    (b) BASELINE config 3's real shape, knapsack n=500 m=200 (700 x 1200 + depth), node-budgeted."""
     from problems import knapsack
+    out = {}
     try:
         p = knapsack(np.random.default_rng(7), 30, 5)
-        for warm_up_mode in (1, 1 | 4):  # also loads the warm-start kernel before anything is timed
+        for warm_up_mode in (1, 1 | 4, 1 | 8):  # loads every kernel before anything is timed
             gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=warm_up_mode, heuristic=1,
                           node_limit=256, keep_log=False)
-        def best_of(mode, reps=3):
+
+        def best_of(prob, mode, limit, reps=3):
             best = None
             for _ in range(reps):
                 t0 = time.perf_counter()
-                res = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=mode, heuristic=1,
-                                    node_limit=8192, keep_log=False)
+                res = gm.milp_solve(prob["c"], None, None, prob["G"], prob["h"], prob["integrality"], mode=mode,
+                                    heuristic=1, node_limit=limit, keep_log=False)
                 el = time.perf_counter() - t0
                 if best is None or el < best[1]:
                     best = (res, el)
             return best
 
-        r, dt = best_of(1)       # wall clock of a host-driven loop of ~14 small launches: best of 3
-        rw, dtw = best_of(1 | 4)
-        return {"nodes_per_sec": r.nodes / dt, "nodes": r.nodes, "waves": r.waves, "pivots": r.pivots,
-                "wall_s": dt, "device_ms": r.device_ms, "gpus": 1,
-                "warm_start": {"nodes_per_sec": rw.nodes / dtw, "nodes": rw.nodes, "pivots": rw.pivots,
-                               "device_ms": rw.device_ms, "note": "GM_BNB_WARM_START: children continue from the "
-                               "parent's basis inverse kept in HBM (not a replay of the reference's cold solves)"},
-                "workload": "0-1 knapsack n=30 m=5 (standard form 35x65 + depth), FIXED mode, most-infeasible "
-                            "branching, node budget 8192, children re-solved from scratch like the reference"}
+        def row(res, dt):
+            return {"nodes_per_sec": res.nodes / dt, "nodes": res.nodes, "waves": res.waves, "pivots": res.pivots,
+                    "wall_s": dt, "device_ms": res.device_ms, "status": res.status}
+
+        out["small"] = {"workload": "0-1 knapsack n=30 m=5 (35x65 + depth), FIXED most-infeasible, node budget 8192, "
+                                    "children solved cold like the reference, best of 3",
+                        "host_replay": row(*best_of(p, 1, 8192)), "device_scan": row(*best_of(p, 1 | 8, 8192)),
+                        "warm_start_host_replay": row(*best_of(p, 1 | 4, 8192))}
+        p3 = knapsack(np.random.default_rng(7), 500, 200)
+        out["c3"] = {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, node "
+                                 "budget 255, device-side scan, cold children", **row(*best_of(p3, 1 | 8, 255, reps=1))}
     except Exception as e:  # never let the extra break the contract line
-        return {"error": str(e)}
+        out["error"] = repr(e)
+    return out
+
+
+def bnb_sharded_extra(gm, dist, dev, rank, world):
+    """B&B frontier sharded over the ranks (gm_comm_init + gm_milp_solve_device): every rank calls with the same
+    arguments, rank r solves the r-th FIFO block of every wave, one ncclAllGather of 32 B per node per wave."""
+    import torch
+    from problems import knapsack
+    try:
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(gm.capi.comm_unique_id()), dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, 0)
+            gm.capi.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        p = knapsack(np.random.default_rng(7), 120, 40)   # 160 x 280 + depth: wide waves of HBM-tier LPs
+        limit = 4095
+        best = None
+        for rep in range(3):
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            r = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=1 | 8, heuristic=1,
+                              node_limit=limit, keep_log=False)
+            dt = time.perf_counter() - t0
+            if rep > 0 and (best is None or dt < best[1]):
+                best = (r, dt)
+        r, dt = best
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if world > 1:
+            gm.capi.comm_destroy()
+        return {"workload": "0-1 knapsack n=120 m=40 seed 7 (160x280 + depth), FIXED most-infeasible, node budget 4095, "
+                            "device-side scan, FIFO blocks per rank, best of 2 after a warm-up run",
+                "gpus": world, "nodes": r.nodes, "waves": r.waves, "pivots": r.pivots, "status": r.status,
+                "wall_s_max_over_ranks": float(t[0]), "nodes_per_sec": r.nodes / float(t[0]), "device_ms": r.device_ms,
+                "collective": "ncclAllGather of 32-byte node records, once per wave" if world > 1 else "none"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def base_config() -> dict:
+    """The workload description both arms print (identical, so that the driver sees the same config)."""
+    return {"workload": WORKLOAD, "m": M, "n": N, "batch_per_gpu": BATCH, "tol": 0.0,
+            "l2": "inputs (275 MB per GPU) exceed the 126 MB L2; no explicit flush",
+            "sharding": "independent LPs, no data-path collective"}
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference's CPU path (oracle/: C++ restatement of Gonum's lp.Simplex, the Go toolchain being absent) on the
+    box's host cores, all of them, on the SAME 4096-LP batch. A step is the whole batch when the run then still ends
+    within a few minutes at the rate measured during warm-up, else the largest prefix of the batch that does."""
     if rank != 0:
         return
     import oracle
     cores = os.cpu_count() or 1
-    per_step = max(16, 8 * cores)
-    c, A, b = make_batch(0, per_step)
-    for _ in range(args.warmup):
-        oracle.simplex_batch(c[:cores], A[:cores], b[:cores], threads=cores)
+    c, A, b = make_batch(0, BATCH)
+    nw = min(BATCH, 8 * cores)
+    rate = None
+    for _ in range(max(1, args.warmup)):
+        t0 = time.perf_counter()
+        oracle.simplex_batch(c[:nw], A[:nw], b[:nw], threads=cores)
+        rate = nw / (time.perf_counter() - t0)
+    per_step = int(min(BATCH, max(8 * cores, rate * 200.0 / max(1, args.steps))))
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.simplex_batch(c, A, b, threads=cores)
+        oracle.simplex_batch(c[:per_step], A[:per_step], b[:per_step], threads=cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} LPs of the workload per step, {cores} threads, one LP per thread"
+    sample = (f"the first {per_step} of the batch's {BATCH} LPs per step, {cores} threads, one LP per thread"
+              if per_step < BATCH else f"the whole {BATCH}-LP batch per step, {cores} threads, one LP per thread")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (BATCH / per_step),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle = C++ restatement of the reference's Gonum lp.Simplex "
-                   "(Go toolchain absent); bounded sample per step"},
+        "config": base_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -303,61 +367,64 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     else:
         pivots_all = pivots
     total_ms, e2e_ms = float(t[0]), float(t[1])
+    # extras, outside the timed region. The sharded B&B is collective: every rank takes part.
+    bnb_sh = bnb_sharded_extra(gm, dist, dev, rank, world)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    smem_peak = gm.capi.microbench_smem_gbs()
+    bnb = bnb_extra(gm) if not args.quick else {"skipped": "--quick"}
+    hbm_tier = hbm_tier_extra(gm) if not args.quick else {"skipped": "--quick"}
 
     value = world * BATCH * args.steps / (total_ms * 1e-3)
     e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     launch_ms = float(np.mean(kernel_ms))
     alg_bytes = pivots * bytes_per_pivot(M, N)  # this rank's launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9  # B/clk/SM crossbar x SMs x clock under load, GB/s
     cores = os.cpu_count() or 1
     n_cpu = min(BATCH, 64 * cores)
     cpu_v, cpu_dt, _ = cpu_baseline(n_cpu, cores)
-    bnb = bnb_extra(gm)
-    hbm_tier = hbm_tier_extra(gm)
     h2d = BATCH * (M * N + M + N) * 8
     d2h = BATCH * (N + 1) * 8 + BATCH * 4 + BATCH * M * 8 + BATCH * 8 * 4
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "m": M, "n": N, "batch_per_gpu": BATCH, "tol": 0.0,
-                   "l2": "inputs (275 MB per GPU) exceed the 126 MB L2; no explicit flush",
-                   "tier": tm["tier"], "grid": tm["grid"], "block": tm["block"], "smem_bytes_per_cta": tm["smem_bytes"],
-                   "pivots_per_lp": pivots / BATCH, "basis_inversions_per_lp": inversions / BATCH,
-                   "sharding": "independent LPs, no data-path collective"},
+        "config": base_config(),
+        "detail": {"tier": tm["tier"], "grid": tm["grid"], "block": tm["block"], "smem_bytes_per_cta": tm["smem_bytes"],
+                   "pivots_per_lp": pivots / BATCH, "basis_inversions_per_lp": inversions / BATCH},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "breakdown_last_step_ms": {"h2d": e2e_tm["h2d_ms"], "kernel": e2e_tm["kernel_ms"], "d2h": e2e_tm["d2h_ms"]},
                 "api": "gm_simplex_batch (C ABI, pinned host buffers)"},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TIER1_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, "
-                                       "profiles/r01_tier1_final_ncu_full_attribution.txt (ncu --set full)", "kernel": "simplex_wave_reg<256,2>" if tm["tier"] == 1 else "simplex_wave_smem<256,2>", "launch_ms": launch_ms,
+        # Tier 1 keeps B^-1 in registers and W in shared memory: the per-pivot bytes never reach HBM (the batch is
+        # read from HBM once per launch), so the roof that bounds this kernel is the SM's shared-memory / issue
+        # bandwidth. `achieved` = SURVEY 8(d)'s algorithmic bytes per pivot x pivots per launch / launch time,
+        # `peak` = the shared-memory bandwidth MEASURED in this run by gm_microbench_smem_gbs.
+        "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+                     "frac": achieved / smem_peak if smem_peak else None, "traffic": None,
+                     "kernel": "simplex_wave_reg", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_pivot": bytes_per_pivot(M, N),
-                     "pivots_per_launch": pivots, "peak_source": peak_src,
-                     "note": "tier 1 keeps B^-1 in registers and W in shared memory, so the algorithmic bytes never "
-                             "touch HBM; the binding resources are issue slots / barrier latency (see smem)",
-                     "smem": {"peak_gbs": smem_peak, "frac": achieved / smem_peak,
-                              "peak_source": "148 SMs x 128 B/clk x median SM clock under load"}},
+                     "pivots_per_launch": pivots,
+                     "peak_source": "measured in this run: all SMs streaming conflict-free 16-byte shared-memory loads "
+                                    "(gm_microbench_smem_gbs); theoretical 148 SMs x 128 B/clk x 1.965 GHz = 37.2 TB/s",
+                     "hbm": {"one_off_bytes_per_launch": BATCH * (M * N + M + N + N + 1 + M) * 8,
+                             "one_off_GBps": BATCH * (M * N + M + N + N + 1 + M) * 8 / (launch_ms * 1e-3) / 1e9,
+                             "peak": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks
+                             else "fallback",
+                             "note": "dram traffic of this kernel is the batch read once + results written once; "
+                                     "ncu dram__bytes captures live under profiles/, not in this line"},
+                     "traffic_note": "null: not captured in this run (no ncu under bench.py); see profiles/ for the "
+                                     "ncu --set full capture of this command"},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {n_cpu} LPs of rank 0's batch, {cores} threads, {cpu_dt:.1f} s"},
         "pivots_per_sec": pivots_all * args.steps / (total_ms * 1e-3),
         "bnb": bnb,
+        "bnb_sharded": bnb_sh,
         "hbm_tier": hbm_tier,
         "clocks": clocks,
     }))
@@ -371,6 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip the B&B / HBM-tier extras (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -380,7 +448,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
-               str(args.warmup), "--impl", args.impl]
+               str(args.warmup), "--impl", args.impl] + (["--quick"] if args.quick else [])
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)

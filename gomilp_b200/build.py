@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libgomilp_b200.so")
-SOURCES = ["engine.cu", "kernels_reg.cu", "kernels_generic.cu", "kernels_coop.cu", "bnb_device.cu", "bnb_host.cpp"]
+SOURCES = ["engine.cu", "kernels_reg.cu", "kernels_generic.cu", "kernels_coop.cu", "bnb_device.cu", "microbench.cu", "bnb_host.cpp"]
 HEADERS = ["simplex_cta.cuh", "cta_rt.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "gomilp_b200.h"),
            os.path.join("..", "..", "include", "gomilp_status.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,6 +21,7 @@ DEPS = {
                   os.path.join(INC, "gomilp_status.h")],
     "bnb_device.cu": ["engine.h", "kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_b200.h"),
                       os.path.join(INC, "gomilp_status.h")],
+    "microbench.cu": ["engine.h", "kernels.h", os.path.join(INC, "gomilp_b200.h"), os.path.join(INC, "gomilp_status.h")],
     "kernels_coop.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
     "kernels_reg.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],
     "kernels_generic.cu": ["kernels.h", "simplex_cta.cuh", "cta_rt.cuh", os.path.join(INC, "gomilp_status.h")],

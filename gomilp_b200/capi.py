@@ -50,7 +50,7 @@ WAVE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_dou
 EXPORTS = ["gm_device_count", "gm_init", "gm_shutdown", "gm_last_error", "gm_last_timing", "gm_set_options",
            "gm_simplex", "gm_simplex_batch", "gm_simplex_batch_device", "gm_upload_root", "gm_free_root",
            "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve", "gm_trace_arm", "gm_trace_fetch",
-           "gm_milp_solve_device", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
+           "gm_milp_solve_device", "gm_microbench_smem_gbs", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
 
 
 def lib():
@@ -78,6 +78,7 @@ def lib():
     L.gm_milp_solve.argtypes = [i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, i32, i64, f64, vp,
                                 C.POINTER(gm_milp_result), DECISION_CB, WAVE_CB, vp]
     L.gm_milp_solve_device.argtypes = L.gm_milp_solve.argtypes
+    L.gm_microbench_smem_gbs.argtypes = [C.POINTER(f64)]
     L.gm_comm_unique_id.argtypes = [vp]
     L.gm_comm_init.argtypes = [i32, i32, vp]
     L.gm_trace_arm.argtypes = [i64, i64]
@@ -307,3 +308,10 @@ def comm_init(rank: int, world: int, uid: bytes):
 
 def comm_destroy():
     lib().gm_comm_destroy()
+
+
+def microbench_smem_gbs() -> float:
+    """Measured shared-memory bandwidth of the current device, GB/s."""
+    v = C.c_double(0.0)
+    _check(lib().gm_microbench_smem_gbs(C.byref(v)))
+    return v.value

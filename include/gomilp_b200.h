@@ -61,6 +61,10 @@ typedef struct gm_options {
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
 
+/* Measured shared-memory bandwidth of the current device in GB/s (all SMs streaming conflict-free 16-byte loads):
+ * the denominator of the roofline of the shared-memory resident tiers (bench.py). */
+int gm_microbench_smem_gbs(double* gbs_out);
+
 /* Pivot trace (parity evidence, BASELINE.json "identical ... branching sequences where pivots tie-break
  * identically"): arm before a host-buffer compute call on this thread; LP `lp_index` of that call records its first
  * `cap` pivots as int32 rows (phase 1|2, entering variable, leaving variable, chosen by replaceBland 0|1) - the

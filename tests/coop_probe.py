@@ -1,0 +1,81 @@
+"""GPU probe (not a test): timings of the cooperative tier on BASELINE's shapes. One JSON line per case."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import gomilp_b200 as gm  # noqa: E402
+from problems import c5_general_integer, feasible_bounded_lp, knapsack, standard_form  # noqa: E402
+
+gm.init(0)
+
+
+def bpp(m, n):
+    return 8 * (3 * m * m + m * (n - m))
+
+
+def run(label, c, A, b, **opt):
+    gm.set_options(**opt)
+    try:
+        t0 = time.perf_counter()
+        g = gm.simplex_batch(c, A, b, want_basis=False)
+        wall = time.perf_counter() - t0
+        tm = gm.last_timing()
+        piv = int(g["pivots"].sum())
+        m, n = A.shape[1:]
+        s = g["stats"] if "stats" in g else None
+        print(json.dumps({"case": label, "count": int(A.shape[0]), "m": m, "n": n, "tier": tm["tier"], "grid": tm["grid"],
+                          "status": sorted(set(int(v) for v in g["status"])), "pivots": piv, "kernel_ms": tm["kernel_ms"],
+                          "us_per_pivot_round": 1e3 * tm["kernel_ms"] / max(1, piv / A.shape[0]),
+                          "alg_GBps": piv * bpp(m, n) / (tm["kernel_ms"] * 1e-3) / 1e9, "wall_s": wall,
+                          "inversions": None if s is None else int(s[:, 3].sum()),
+                          "bland": None if s is None else int(s[:, 2].sum())}), flush=True)
+        return g
+    finally:
+        gm.set_options()
+
+
+rng = np.random.default_rng(1)
+c, A, b = feasible_bounded_lp(rng, 40, 90, 4)
+run("small forced tier 6", c, A, b, force_tier=6, coop_group=4)
+c, A, b = feasible_bounded_lp(rng, 150, 300, 1)
+run("150x300 x1 auto", c, A, b)
+run("150x300 x1 tier 3", c, A, b, force_tier=3)
+c, A, b = feasible_bounded_lp(rng, 150, 300, 16)
+run("150x300 x16 auto", c, A, b)
+c, A, b = feasible_bounded_lp(rng, 400, 800, 1)
+run("400x800 x1 auto", c, A, b)
+lps = [feasible_bounded_lp(np.random.default_rng(42 + k), 1024, 2048) for k in range(16)]
+c = np.stack([l[0] for l in lps]); A = np.stack([l[1] for l in lps]); b = np.stack([l[2] for l in lps])
+run("C4 single", c[:1], A[:1], b[:1])
+run("C4 single G=64", c[:1], A[:1], b[:1], coop_group=64)
+run("C4 single G=32", c[:1], A[:1], b[:1], coop_group=32)
+run("C4 batch16", c, A, b)
+run("C4 batch4", c[:4], A[:4], b[:4])
+# C3 root + one child through the wave API
+p = knapsack(np.random.default_rng(7), 500, 200)
+c0, A0, b0 = standard_form(p)
+root = gm.upload_root(c0, A0, b0)
+for L, bv, bs, br in ((0, np.zeros((1, 0), np.int32), np.zeros((1, 0)), np.zeros((1, 0))),):
+    t0 = time.perf_counter()
+    w = gm.solve_wave(root, A0.shape[1], A0.shape[0], bv, bs, br)
+    tm = gm.last_timing()
+    print(json.dumps({"case": "C3 root wave", "tier": tm["tier"], "grid": tm["grid"], "status": int(w.status[0]),
+                      "z": float(w.z[0]), "pivots": int(w.stats[0, 0] + w.stats[0, 1]), "bland": int(w.stats[0, 2]),
+                      "kernel_ms": tm["kernel_ms"], "wall_s": time.perf_counter() - t0}), flush=True)
+x = w.x[0]
+frac = np.abs(x[:500] - np.round(x[:500]))
+j = int(np.argmax(frac))
+bv = np.array([[j], [j]], np.int32); bs = np.array([[1.0], [-1.0]]); br = np.array([[np.floor(x[j])], [-(np.floor(x[j]) + 1)]])
+t0 = time.perf_counter()
+w = gm.solve_wave(root, A0.shape[1], A0.shape[0], bv, bs, br)
+tm = gm.last_timing()
+print(json.dumps({"case": "C3 depth-1 wave (2 nodes)", "tier": tm["tier"], "grid": tm["grid"], "status": w.status.tolist(),
+                  "z": w.z.tolist(), "pivots": (w.stats[:, 0] + w.stats[:, 1]).tolist(), "bland": w.stats[:, 2].tolist(),
+                  "kernel_ms": tm["kernel_ms"], "wall_s": time.perf_counter() - t0}), flush=True)
+gm.free_root(root)

@@ -1,0 +1,100 @@
+"""Multi-GPU branch-and-bound through the C ABI (gm_comm_init + gm_milp_solve_device): one process per GPU, the NCCL id
+travels through a multiprocessing pipe. Prints one JSON line per configuration; exits non-zero when the ranks disagree
+with each other or with the 1-GPU run.   python tests/multi_gpu_probe.py --world 2 [--n 40 --m 6 --nodes 8192]"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def problem(kind, n, m, seed):
+    from problems import c5_general_integer, knapsack
+    if kind == "c5":
+        return c5_general_integer(n)
+    return knapsack(np.random.default_rng(seed), n, m)
+
+
+def worker(rank, world, conn, args):
+    import gomilp_b200 as gm
+    from gomilp_b200 import status as S
+    gm.init(rank)
+    if world > 1:
+        if rank == 0:
+            uid = gm.capi.comm_unique_id()
+            conn.send(uid)
+        uid = conn.recv()
+        gm.capi.comm_init(rank, world, uid)
+    p = problem(args.kind, args.n, args.m, args.seed)
+    mode = S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN
+    out = None
+    for rep in range(args.reps + 1):  # first repetition warms the kernels / NCCL up
+        t0 = time.perf_counter()
+        r = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=mode, heuristic=1,
+                          node_limit=args.nodes, keep_log=(rep == 0 and args.log))
+        dt = time.perf_counter() - t0
+        if out is None or dt < out["wall_s"]:
+            out = {"rank": rank, "status": r.status, "lp_status": r.lp_status, "nodes": r.nodes, "waves": r.waves,
+                   "pivots": r.pivots, "z": r.z, "x": None if r.x is None else r.x.tolist(), "wall_s": dt,
+                   "device_ms": r.device_ms, "log": r.log if rep == 0 else out.get("log", [])}
+        if rep == 0:
+            out["log"] = r.log
+    if world > 1:
+        gm.capi.comm_destroy()
+    conn.send(out)
+
+
+def run(world, args):
+    ctx = mp.get_context("spawn")
+    pipes = [ctx.Pipe() for _ in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, pipes[r][1], args)) for r in range(world)]
+    [p.start() for p in procs]
+    if world > 1:
+        uid = pipes[0][0].recv()
+        for r in range(world):
+            pipes[r][0].send(uid)
+    outs = [pipes[r][0].recv() for r in range(world)]
+    [p.join() for p in procs]
+    return outs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--world", type=int, default=2)
+    ap.add_argument("--kind", default="knapsack")
+    ap.add_argument("--n", type=int, default=40)
+    ap.add_argument("--m", type=int, default=6)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--nodes", type=int, default=8192)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--log", type=int, default=1)
+    args = ap.parse_args()
+    one = run(1, args)[0]
+    many = run(args.world, args) if args.world > 1 else [one]
+    ok = True
+    for o in many:
+        same = (o["status"], o["lp_status"], o["nodes"], o["waves"], o["pivots"], o["z"], o["x"]) == \
+               (one["status"], one["lp_status"], one["nodes"], one["waves"], one["pivots"], one["z"], one["x"])
+        same = same and (not args.log or o["log"] == one["log"])
+        ok = ok and same
+    wall = max(o["wall_s"] for o in many)
+    print(json.dumps({"workload": f"{args.kind} n={args.n} m={args.m} seed={args.seed} FIXED most-infeasible, node budget "
+                      f"{args.nodes}, device-side scan", "world": args.world, "identical_to_1gpu": ok,
+                      "status": one["status"], "lp_status": one["lp_status"], "nodes": one["nodes"], "waves": one["waves"],
+                      "pivots": one["pivots"], "nodes_per_sec_1gpu": one["nodes"] / one["wall_s"],
+                      "nodes_per_sec": one["nodes"] / wall, "wall_s_1gpu": one["wall_s"], "wall_s": wall,
+                      "device_ms_1gpu": one["device_ms"], "device_ms": max(o["device_ms"] for o in many)}))
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,290 @@
+"""GPU (-m gpu): parity at BASELINE.json's configured shapes against the committed oracle fixtures
+(tests/golden/*.npz, generated once by tests/golden/make_config_fixtures.py from the CPU oracle), on the tier each
+shape really selects; the rarely-taken solver paths forced and counted; decision logs replayed node by node under
+equal budgets with the first divergence classified. Tolerance: 1e-9 relative on objectives and primal values.
+A human-readable report goes to gpurun_out/r02_parity_report.txt (copied to profiles/ when it changes)."""
+import hashlib
+import os
+import time
+
+import numpy as np
+import pytest
+
+import gomilp_b200 as gm
+import oracle
+from gomilp_b200 import status as S
+from parity_tools import classify_divergence, compare_bnb_logs, first_divergence
+from problems import c5_general_integer, feasible_bounded_lp, knapsack, node_lp, standard_form
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+RTOL = 1e-9
+
+
+def report(line: str):
+    print(line)
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r02_parity_report.txt"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def _wave_fixture_check(name, c0, A0, b0, expect_tier=None, force_tier=0, only_depth=None):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    assert str(z["A0_sha"]) == sha(A0), "generator drift: regenerate the fixture"
+    m0, n0 = A0.shape
+    root = gm.upload_root(c0, A0, b0)
+    worst_z = worst_x = 0.0
+    same_piv = total = bland_nodes = bland_fired = repair_nodes = repair_fired = 0
+    tiers = set()
+    t_dev = 0.0
+    try:
+        if force_tier:
+            gm.set_options(force_tier=force_tier)
+        for L in sorted(set(int(v) for v in z["L"])):
+            if only_depth is not None and L not in only_depth:
+                continue
+            idx = np.nonzero(z["L"] == L)[0]
+            bvar = z["bvar"][idx, :L].astype(np.int32).reshape(len(idx), L)
+            w = gm.solve_wave(root, n0, m0, bvar, z["bsign"][idx, :L].reshape(len(idx), L),
+                              z["brhs"][idx, :L].reshape(len(idx), L))
+            tm = gm.last_timing()
+            tiers.add(tm["tier"])
+            t_dev += tm["kernel_ms"]
+            for q, k in enumerate(idx):
+                total += 1
+                assert w.status[q] == int(z["status"][k]), (name, L, q, w.status[q], int(z["status"][k]))
+                if int(z["status"][k]) == S.GM_OK:
+                    worst_z = max(worst_z, rel(w.z[q], z["z"][k]))
+                    worst_x = max(worst_x, rel(w.x[q], z["x"][k]))
+                piv = int(w.stats[q, 0] + w.stats[q, 1])
+                same_piv += int(piv == int(z["piv1"][k] + z["piv2"][k]))
+                bland_nodes += int(z["bland"][k] > 0)
+                bland_fired += int(z["bland"][k] > 0 and w.stats[q, 2] > 0)
+                repair_nodes += int(z["repair"][k] > 0)
+                repair_fired += int(z["repair"][k] > 0 and w.stats[q, 6] > 0)
+    finally:
+        gm.set_options()
+        gm.free_root(root)
+    report(f"{name} ({m0}x{n0}+L) tier {sorted(tiers)}: {total} node LPs, status equal, max rel err z {worst_z:.2e} "
+           f"x {worst_x:.2e}; same pivot count {same_piv}/{total}; Bland fired on {bland_fired}/{bland_nodes} nodes "
+           f"where the oracle's did, repair loop {repair_fired}/{repair_nodes}; device {t_dev:.1f} ms")
+    assert worst_z <= RTOL and worst_x <= RTOL
+    if expect_tier is not None:
+        assert expect_tier in tiers
+    return tiers
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n", [50, 100, 200, 400])
+def test_c5_general_integer_fixture(n):
+    """Config C5: general-integer sweep, bounds as rows. Roots and children against the oracle."""
+    p = c5_general_integer(n)
+    c0, A0, b0 = standard_form(p)
+    _wave_fixture_check(f"c5_general_n{n}", c0, A0, b0, expect_tier=2 if n == 50 else 6)
+    if n in (100, 200):  # the one-CTA-per-LP tiers on the same shape
+        _wave_fixture_check(f"c5_general_n{n}", c0, A0, b0, force_tier=3 if n == 100 else 4, only_depth=(0, 1))
+
+
+@pytest.mark.timeout(1200)
+def test_c3_knapsack_fixture():
+    """Config C3: 0-1 knapsack n=500 m=200 (standard form 700 x 1200): root + the first three waves."""
+    p = knapsack(np.random.default_rng(7), 500, 200)
+    c0, A0, b0 = standard_form(p)
+    _wave_fixture_check("c3_knapsack", c0, A0, b0, expect_tier=6)
+    _wave_fixture_check("c3_knapsack", c0, A0, b0, force_tier=4, only_depth=(0,))
+
+
+@pytest.mark.timeout(1200)
+def test_c4_single_large_lp():
+    """Config C4: one dense LP 1024 x 2048, seed 42, on the whole GPU (cooperative tier, all SMs on one LP)."""
+    z = np.load(os.path.join(GOLD, "c4_large_lp.npz"))
+    m, n = int(z["m"]), int(z["n"])
+    c, A, b = feasible_bounded_lp(np.random.default_rng(int(z["seed"])), m, n)
+    assert str(z["A_sha"]) == sha(A), "generator drift: regenerate the fixture"
+    cap = int(z["cold_cap"])
+    gm.trace_arm(0, 4096)
+    t0 = time.perf_counter()
+    r = gm.simplex(c, A, b)
+    wall = time.perf_counter() - t0
+    tm = gm.last_timing()
+    tr = gm.trace_fetch(4096)
+    assert tm["tier"] == 6 and tm["grid"] >= 128
+    assert r.status == S.GM_OK
+    ez, ex = rel(r.optF, z["z"]), rel(r.x, z["x"])
+    same_basis = set(int(v) for v in r.basis) == set(int(v) for v in z["opt_basis"])
+    # the oracle's own cold start: basis scan + its first pivots
+    tr_ref = z["cold_trace"]
+    d = first_divergence(tr_ref, tr[: len(tr_ref)])
+    why = "identical"
+    if d >= 0:
+        why = classify_divergence(c, A, b, tr_ref, tr, d, np.arange(n - 1, n - 1 - m, -1))
+    report(f"c4_large_lp 1024x2048 tier 6 grid {tm['grid']}: status OK, rel err z {ez:.2e} x {ex:.2e} vs the oracle on "
+           f"the optimal basis (HiGHS z {float(z['highs_z'])!r}); optimal basis identical: {same_basis}; {r.pivots} pivots, "
+           f"kernel {tm['kernel_ms']:.1f} ms ({1e3 * tm['kernel_ms'] / max(1, r.pivots):.1f} us/pivot), wall {wall:.2f} s; first "
+           f"{len(tr_ref)} pivots vs the oracle's cold start: {why} (first difference at {d})")
+    assert ez <= RTOL and ex <= RTOL and same_basis
+    assert why != "REAL"
+    # a batch of 16 copies (groups of 9 CTAs): every copy must reproduce the single solve bit for bit
+    k = 16
+    g = gm.simplex_batch(np.tile(c, (k, 1)), np.tile(A, (k, 1, 1)), np.tile(b, (k, 1)))
+    tm = gm.last_timing()
+    assert tm["tier"] == 6 and (g["status"] == S.GM_OK).all()
+    assert rel(g["optF"], np.full(k, float(z["z"]))) <= RTOL and rel(g["x"], np.tile(z["x"], (k, 1))) <= RTOL
+    piv = int(g["pivots"].sum())
+    bpp = 8 * (3 * m * m + m * (n - m))
+    report(f"c4 batch of 16 (tier 6, {tm['grid'] // 16} CTAs per LP): {piv} pivots in {tm['kernel_ms']:.1f} ms = "
+           f"{piv * bpp / (tm['kernel_ms'] * 1e-3) / 1e9:.0f} GB/s algorithmic")
+
+
+def test_forced_bland_repair_and_scan_paths():
+    """The rarely-taken paths of simplex.go - replaceBland :347-383, the artificial-still-basic repair loop :581-606,
+    column rejection in findLinearlyIndependent :611-637 - on LPs where the ORACLE takes them (forced_paths.npz):
+    same status / objective, the same machinery runs (stats[2] Bland calls, stats[6] repair trials, stats[5] basis
+    scan), and any difference between the pivot sequences is a near-tie in the quantity floats.MinIdx compared."""
+    z = np.load(os.path.join(GOLD, "forced_paths.npz"))
+    for tier in (1, 2, 6):
+        fired = {"bland": 0, "repair": 0, "scan": 0}
+        whys, ident = [], 0
+        try:
+            gm.set_options(force_tier=tier, coop_group=3 if tier == 6 else 0)
+            for kind in ("bland", "repair", "scan"):
+                for k in range(int(z[kind + "_count"])):
+                    c, A, b = z[f"{kind}{k}_c"], z[f"{kind}{k}_A"], z[f"{kind}{k}_b"]
+                    gm.trace_arm(0, 256)
+                    g = gm.simplex_batch(c[None], A[None], b[None])
+                    tr = gm.trace_fetch(256)
+                    s = g["stats"][0]
+                    zr = float(z[f"{kind}{k}_z"])
+                    assert g["status"][0] == int(z[f"{kind}{k}_status"])
+                    assert abs(g["optF"][0] - zr) <= RTOL * max(1.0, abs(zr))
+                    assert rel(g["x"][0], z[f"{kind}{k}_x"]) <= 1e-7  # degenerate optima may have a face of solutions
+                    fired["bland"] += int(s[2] > 0)
+                    fired["repair"] += int(s[6] > 0)
+                    fired["scan"] += int(s[5] > 0)
+                    if kind == "scan":
+                        assert s[5] == 1
+                    tr_ref = z[f"{kind}{k}_trace"]
+                    d = first_divergence(tr_ref, tr)
+                    ident += int(d < 0)
+                    if d >= 0:
+                        why = classify_divergence(c, A, b, tr_ref, tr, d, oracle.initial_basis(A), z[f"{kind}{k}_basis"])
+                        whys.append(why)
+                        assert why != "REAL", (tier, kind, k, d)
+        finally:
+            gm.set_options()
+        report(f"forced paths, tier {tier}: of 18 LPs Bland fired on {fired['bland']}, repair loop on {fired['repair']}, "
+               f"basis scan on {fired['scan']}; pivot trace identical to the oracle's on {ident}, else first divergence "
+               f"is {({w: whys.count(w) for w in sorted(set(whys))})}")
+        assert fired["bland"] >= 4 and fired["repair"] >= 3 and fired["scan"] >= 6
+
+
+@pytest.mark.timeout(900)
+def test_c1_milps_decision_logs_under_equal_budgets():
+    """Config C1: 100 small MILPs (seed 155), COMPAT and FIXED replays with the SAME node budget on both sides. Status,
+    objective and x at 1e-9; decision logs compared node by node; the host replay and the device-side scan must agree
+    with each other exactly."""
+    z = np.load(os.path.join(GOLD, "c1_milps.npz"))
+    budget, count = int(z["budget"]), int(z["count"])
+    for mode in (S.GM_BNB_COMPAT, S.GM_BNB_FIXED):
+        same_status = same_tree = ok_both = 0
+        why = {}
+        worst = 0.0
+        for k in range(count):
+            A = z[f"p{k}_A"] if f"p{k}_A" in z else None
+            bb = z[f"p{k}_b"] if f"p{k}_b" in z else None
+            args = (z[f"p{k}_c"], A, bb, z[f"p{k}_G"], z[f"p{k}_h"], z[f"p{k}_integ"])
+            g = gm.milp_solve(*args, heuristic=1, mode=mode, node_limit=budget)
+            dv = gm.milp_solve(*args, heuristic=1, mode=mode | S.GM_BNB_DEVICE_SCAN, node_limit=budget)
+            # the two schedulers of this repo see the same LP results: they must agree exactly
+            assert (dv.status, dv.lp_status, dv.nodes, dv.pivots) == (g.status, g.lp_status, g.nodes, g.pivots), k
+            assert dv.log == g.log, k
+            if g.x is not None:
+                assert np.array_equal(dv.x, g.x) and dv.z == g.z
+            pre = f"p{k}_m{mode}_"
+            st_o = int(z[pre + "status"])
+            same_status += int(g.status == st_o)
+            ref_log = {key: z[pre + "log_" + key] for key in ("id", "parent", "lp_status", "z", "decision",
+                                                              "branch_var", "branch_floor")}
+            ident, node, reason = compare_bnb_logs(ref_log, g.log)
+            same_tree += int(ident and g.status == st_o and g.nodes == int(z[pre + "nodes"]))
+            if not ident:
+                key = reason.split(" ")[0]
+                why[key] = why.get(key, 0) + 1
+            if st_o == S.GM_MILP_OK and g.status == S.GM_MILP_OK:
+                ok_both += 1
+                worst = max(worst, rel(g.z, z[pre + "z"]), rel(g.x, z[pre + "x"]))
+        report(f"C1 mode {'COMPAT' if mode == 0 else 'FIXED'}: {count} MILPs, budget {budget}: same status {same_status}, "
+               f"identical decision log {same_tree}, both optimal {ok_both} with max rel err {worst:.2e}; first "
+               f"divergences by kind {why}; host replay == device scan on all")
+        assert worst <= RTOL
+        assert same_status >= int(0.8 * count) and same_tree >= int(0.6 * count)
+
+
+@pytest.mark.timeout(600)
+def test_c5_bnb_replay_against_oracle_logs():
+    for n, budget in ((50, 64), (100, 32)):
+        z = np.load(os.path.join(GOLD, f"c5_general_n{n}.npz"))
+        p = c5_general_integer(n)
+        for extra, label in ((0, "host replay"), (S.GM_BNB_DEVICE_SCAN, "device scan")):
+            g = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], heuristic=1,
+                              mode=S.GM_BNB_FIXED | extra, node_limit=budget)
+            ref_log = {"id": z["bnb_log_id"], "parent": z["bnb_log_parent"], "lp_status": z["bnb_log_lp_status"],
+                       "z": z["bnb_log_z"], "decision": z["bnb_log_decision"], "branch_var": z["bnb_log_branch_var"],
+                       "branch_floor": z["bnb_log_branch_floor"]}
+            ident, node, reason = compare_bnb_logs(ref_log, g.log)
+            report(f"C5 n={n} B&B, budget {budget}, {label}: status {g.status} (oracle {int(z['bnb_status'])}), nodes "
+                   f"{g.nodes} (oracle {int(z['bnb_nodes'])}), decision log identical: {ident} {reason if not ident else ''}")
+            assert g.status == int(z["bnb_status"]) and g.nodes == int(z["bnb_nodes"])
+            assert ident, (node, reason)
+
+
+@pytest.mark.timeout(600)
+def test_device_scan_equals_host_replay_on_knapsack():
+    rng = np.random.default_rng(8)
+    for (n, m, lim, heur) in ((24, 4, 600, 1), (30, 5, 3000, 1), (18, 3, 400, 0), (18, 3, 400, 2)):
+        p = knapsack(rng, n, m)
+        a = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, heuristic=heur,
+                          node_limit=lim)
+        d = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                          mode=S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN, heuristic=heur, node_limit=lim)
+        assert (a.status, a.lp_status, a.nodes, a.waves, a.pivots) == (d.status, d.lp_status, d.nodes, d.waves, d.pivots)
+        assert a.log == d.log
+        if a.x is not None:
+            assert np.array_equal(a.x, d.x) and a.z == d.z
+
+
+def test_two_host_threads_on_one_device_do_not_interfere():
+    """Concurrent callers with different shapes (launch attributes used to be set per launch)."""
+    import threading
+    rng = np.random.default_rng(21)
+    sets = [feasible_bounded_lp(rng, m, n, 48) for (m, n) in ((40, 90), (100, 180), (64, 128), (150, 260))]
+    want = [gm.simplex_batch(*s) for s in sets]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(4):
+                g = gm.simplex_batch(*sets[i])
+                assert np.array_equal(g["status"], want[i]["status"]) and np.array_equal(g["x"], want[i]["x"])
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(sets))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
