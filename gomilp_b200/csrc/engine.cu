@@ -143,11 +143,11 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
     const gm::WsLayout w2 = gm::ws_layout(m, n, kHbmThreads, false, true);
     const size_t smem_reg = wr.big_bytes + wr.small_bytes;
     const size_t smem_all = w1.big_bytes + w1.small_bytes;
-    const bool fits_reg = m <= 64 && smem_reg + 64 <= d.smem_optin;
-    const bool fits_smem = smem_all + 64 <= d.smem_optin;
-    const bool fits_small = w2.small_bytes + 64 <= d.smem_optin;
+    const bool fits_reg = m <= 64 && smem_reg + 256 <= d.smem_optin;
+    const bool fits_smem = smem_all + 256 <= d.smem_optin;
+    const bool fits_small = w2.small_bytes + 256 <= d.smem_optin;
     const size_t bi_bytes = (w3.big_doubles - w3.Bi) * sizeof(double);
-    const bool fits_bismem = bi_bytes + w3.small_bytes + 64 <= d.smem_optin;
+    const bool fits_bismem = bi_bytes + w3.small_bytes + 256 <= d.smem_optin;
     // tier 6 (cooperative): fewer LPs than SMs and an LP big enough that one CTA per LP would crawl
     int G = 0;
     if (d.coop_ok && m < n) {

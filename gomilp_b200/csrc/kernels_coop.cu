@@ -15,7 +15,11 @@ __global__ void __launch_bounds__(gm_kernels::kHbmThreads, 1) simplex_wave_coop(
 
 namespace gm_kernels {
 cudaError_t coop_prepare(size_t smem_max) {
-    return cudaFuncSetAttribute(simplex_wave_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, simplex_wave_coop);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(simplex_wave_coop, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(smem_max - a.sharedSizeBytes));
 }
 cudaError_t coop_occupancy(int block, size_t smem, int* ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_coop, block, smem);

@@ -33,7 +33,11 @@ __global__ void __launch_bounds__(gm_kernels::kHbmThreads, 1) simplex_wave_gener
 
 namespace gm_kernels {
 cudaError_t generic_set_smem_limit(size_t smem_max) {
-    return cudaFuncSetAttribute(simplex_wave_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, simplex_wave_generic);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(simplex_wave_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(smem_max - a.sharedSizeBytes));
 }
 cudaError_t generic_prepare(int block, size_t smem, int* ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_generic, block, smem);

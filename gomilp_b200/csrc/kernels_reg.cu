@@ -19,10 +19,18 @@ __global__ void __launch_bounds__(gm_kernels::kSmemThreads, 2) simplex_wave_reg_
 }  // namespace
 
 namespace gm_kernels {
-cudaError_t reg_set_smem_limit(size_t smem_max) {
-    cudaError_t e = cudaFuncSetAttribute(simplex_wave_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+// the dynamic limit is the opt-in maximum minus the kernel's static shared memory
+template <class K>
+static cudaError_t raise_limit(K kernel, size_t smem_max) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(simplex_wave_reg_warm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_max - a.sharedSizeBytes));
+}
+cudaError_t reg_set_smem_limit(size_t smem_max) {
+    cudaError_t e = raise_limit(simplex_wave_reg, smem_max);
+    if (e != cudaSuccess) return e;
+    return raise_limit(simplex_wave_reg_warm, smem_max);
 }
 cudaError_t reg_prepare(size_t smem, int* ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_reg, kSmemThreads, smem);
