@@ -7,9 +7,10 @@ compute call raises.
 """
 from . import capi  # noqa: F401
 from .capi import (EngineError, LPResult, WaveResult, MilpResult, simplex, simplex_batch, simplex_batch_device,
-                   upload_root, free_root, solve_wave, milp_solve, last_timing, set_options, device_count, init)
+                   upload_root, free_root, solve_wave, milp_solve, last_timing, set_options, device_count, init,
+                   trace_arm, trace_fetch, profile_arm, profile_fetch)
 from .status import *  # noqa: F401,F403
 
 __all__ = ["EngineError", "LPResult", "WaveResult", "MilpResult", "simplex", "simplex_batch",
            "simplex_batch_device", "upload_root", "free_root", "solve_wave", "milp_solve", "last_timing",
-           "set_options", "device_count", "init"]
+           "set_options", "device_count", "init", "trace_arm", "trace_fetch", "profile_arm", "profile_fetch"]

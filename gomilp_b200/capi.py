@@ -50,7 +50,7 @@ WAVE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_dou
 EXPORTS = ["gm_device_count", "gm_init", "gm_shutdown", "gm_last_error", "gm_last_timing", "gm_set_options",
            "gm_simplex", "gm_simplex_batch", "gm_simplex_batch_device", "gm_upload_root", "gm_free_root",
            "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve", "gm_trace_arm", "gm_trace_fetch",
-           "gm_milp_solve_device", "gm_microbench_smem_gbs", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
+           "gm_milp_solve_device", "gm_microbench_smem_gbs", "gm_profile_arm", "gm_profile_fetch", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
 
 
 def lib():
@@ -87,6 +87,8 @@ def lib():
         if name != "gm_last_error":
             getattr(L, name).restype = C.c_int
     L.gm_trace_fetch.restype = C.c_int64
+    L.gm_profile_fetch.argtypes = [vp, i64]
+    L.gm_profile_fetch.restype = C.c_int64
     _lib = L
     return L
 
@@ -315,3 +317,14 @@ def microbench_smem_gbs() -> float:
     v = C.c_double(0.0)
     _check(lib().gm_microbench_smem_gbs(C.byref(v)))
     return v.value
+
+
+def profile_arm():
+    """Cooperative tier: the next host-buffer compute call reports per-LP leader clock cycles (see gm_profile_arm)."""
+    _check(lib().gm_profile_arm())
+
+
+def profile_fetch(lps: int = 1) -> np.ndarray:
+    out = np.zeros((lps, 8), dtype=np.int64)
+    k = lib().gm_profile_fetch(_p(out), lps)
+    return out[:k]

@@ -37,6 +37,7 @@ GM_DEV double gm_ldg(const double* p) { return __ldg(p); }
 GM_DEV int gm_block_id() { return (int)blockIdx.x; }
 GM_DEV void gm_threadfence() { __threadfence(); }
 GM_DEV void gm_spin_pause() {}
+GM_DEV long long gm_clock() { return clock64(); }
 GM_DEV void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 GM_DEV unsigned long long gm_ld_acquire_u64(const unsigned long long* p) {
     unsigned long long v;

@@ -156,7 +156,7 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
         G = std::min(G, d.sms);
         if ((long long)G * P.count > d.sms) G = d.sms / P.count;
     }
-    const gm::CoopLayout cl = gm::coop_layout(m, n, kHbmThreads, G > 0 ? G : 1);
+    const gm::CoopLayout cl = gm::coop_layout(m, n, kHbmThreads, G > 0 ? G : 1, d.smem_optin - 512);
     const bool fits_coop = G >= 1 && cl.smem_bytes + 256 <= d.smem_optin;
     int tier = opt.force_tier;
     if (tier == 0) {
@@ -204,6 +204,15 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
         block = kHbmThreads;
         P.hbm_layout = 1;
         P.coop_G = G;
+        P.coop_pan = cl.pan_nb;
+        if (t_trace.prof_armed && !t_trace.prof_in_flight) {  // leader clock cycles per activity (gm_profile_arm)
+            CK(cudaMallocAsync(&t_trace.d_prof, sizeof(long long) * 8 * (size_t)P.count, stream));
+            CK(cudaMemsetAsync(t_trace.d_prof, 0, sizeof(long long) * 8 * (size_t)P.count, stream));
+            P.prof = t_trace.d_prof;
+            t_trace.prof_count = P.count;
+            t_trace.prof_in_flight = true;
+            t_trace.prof_stream = stream;
+        }
         const int groups = std::min(P.count, d.sms / G);
         grid = groups * G;
         smem = cl.smem_bytes;
@@ -263,6 +272,16 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
 
 // Called by the host-buffer entry points once their stream has been synchronised: brings an armed trace back.
 void finish_trace() {
+    if (t_trace.prof_in_flight) {
+        t_trace.prof.assign((size_t)t_trace.prof_count * 8, 0);
+        cudaMemcpyAsync(t_trace.prof.data(), t_trace.d_prof, sizeof(long long) * 8 * (size_t)t_trace.prof_count,
+                        cudaMemcpyDeviceToHost, t_trace.prof_stream);
+        cudaStreamSynchronize(t_trace.prof_stream);
+        cudaFreeAsync(t_trace.d_prof, t_trace.prof_stream);
+        t_trace.prof_in_flight = false;
+        t_trace.prof_armed = false;
+        t_trace.d_prof = nullptr;
+    }
     if (!t_trace.in_flight) return;
     t_trace.rows.assign((size_t)t_trace.cap * 4, -1);
     cudaMemcpyAsync(t_trace.rows.data(), t_trace.d_buf, sizeof(int) * 4 * (size_t)t_trace.cap, cudaMemcpyDeviceToHost,
@@ -346,6 +365,20 @@ int gm_trace_arm(int64_t lp_index, int64_t cap) {
     t_trace.cap = cap;
     t_trace.rows.clear();
     return GM_OK;
+}
+
+int gm_profile_arm(void) {
+    t_trace.prof_armed = true;
+    t_trace.prof_in_flight = false;
+    t_trace.prof.clear();
+    return GM_OK;
+}
+
+int64_t gm_profile_fetch(int64_t* out, int64_t lps) {
+    if (!out) return 0;
+    const int64_t k = std::min<int64_t>(lps, (int64_t)t_trace.prof.size() / 8);
+    std::memcpy(out, t_trace.prof.data(), sizeof(int64_t) * 8 * (size_t)k);
+    return k;
 }
 
 int64_t gm_trace_fetch(int32_t* out, int64_t cap) {

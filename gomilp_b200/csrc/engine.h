@@ -69,6 +69,12 @@ struct TraceReq {
     int* d_buf = nullptr;
     cudaStream_t stream = nullptr;
     std::vector<int32_t> rows;
+    // gm_profile_arm: leader clock cycles per activity of the cooperative tier
+    bool prof_armed = false, prof_in_flight = false;
+    long long* d_prof = nullptr;
+    int64_t prof_count = 0;
+    cudaStream_t prof_stream = nullptr;
+    std::vector<long long> prof;
 };
 
 extern Engine g;

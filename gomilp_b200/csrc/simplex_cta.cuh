@@ -83,7 +83,9 @@ struct BatchParams {
     int trace_cap, trace_lp;
     // ---- cooperative tier (6): `coop_G` CTAs of one cooperative launch work on one LP (simplex_wave_coop) --------
     int coop_G;                     // CTAs per group
+    int coop_pan;                   // inversion panel width when the panel fits in shared memory (16), else 0
     unsigned long long* coop_bar;   // [groups] barrier counters, zeroed before launch
+    long long* prof;                // optional [count][8]: leader clock cycles spent per activity (see coop_cta_main)
 };
 
 // Workspace of one CTA, split in a "big" part (W and Bi: O(mn) doubles) and a "small" part (vectors,
@@ -170,11 +172,12 @@ struct MinLoc {
 struct CoopLayout {
     size_t Bi1, Tp, Rs, mail, group_doubles;              // HBM, relative to the group's slice
     size_t s_y, s_prow, s_ae, s_xb, s_al, s_f, s_r, s_part, s_red, s_bit, s_redi, smem_bytes;  // shared memory
+    int pan_nb;  // 16: the inversion panel lives in shared memory (aliasing the main-loop scratch); 0: in HBM, 32 wide
 };
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline CoopLayout coop_layout(int m, int n, int T, int G) {
+inline CoopLayout coop_layout(int m, int n, int T, int G, size_t smem_limit = 200 * 1024) {
     const WsLayout w = ws_layout(m, n, T, false, true);
     CoopLayout c;
     auto up4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
@@ -182,7 +185,7 @@ inline CoopLayout coop_layout(int m, int n, int T, int G) {
     c.Bi1 = o; o = up4(o + (size_t)m * w.ldb);
     c.Tp = o; o = up4(o + (size_t)m * 32);
     c.Rs = o; o = up4(o + (size_t)32 * w.ldb);
-    c.mail = o; o = up4(o + 16 + 8 * (size_t)G);
+    c.mail = o; o = up4(o + 16 + 12 * (size_t)G);
     c.group_doubles = o;
     const size_t mp = (size_t)((m + 3) & ~3);
     const size_t rlen = (size_t)(((n + 1 - m) > m ? (n + 1 - m) : m) + 4) & ~(size_t)3;
@@ -195,6 +198,12 @@ inline CoopLayout coop_layout(int m, int n, int T, int G) {
     c.s_f = q; q += mp;
     c.s_r = q; q += rlen;
     c.s_part = q; q += (size_t)T + mp;
+    // The inversion panel (m x 17 doubles, 16 columns + 1 of padding) plus a column and a row vector ALIAS the
+    // main-loop scratch above: an inversion only runs between main-loop calls, when all of it is dead.
+    const size_t pan = (size_t)m * 17 + mp + 32;
+    const size_t tail = (size_t)T + (mp + 1) / 2 + ((size_t)T + 1) / 2;
+    c.pan_nb = ((pan > q ? pan : q) + tail) * sizeof(double) + 1024 <= smem_limit ? 16 : 0;
+    if (c.pan_nb && pan > q) q = pan;
     c.s_red = q; q += (size_t)T;
     c.s_bit = q; q += (mp + 1) / 2;     // ints
     c.s_redi = q; q += ((size_t)T + 1) / 2;  // ints
@@ -242,6 +251,9 @@ struct SolverT {
     double *Bi1, *Tp, *Rs;        // second buffer of the inverse; inversion panel (m x CNB) and pivot-row snapshot
     double *s_y, *s_prow, *s_ae, *s_xb, *s_al, *s_f, *s_r, *s_part;  // shared-memory scratch of this CTA
     int* s_bit;
+    double* s_pan;                // shared-memory inversion panel (aliases the scratch above), nullptr: use Tp
+    long long prof_t[8];          // leader: clock cycles in solve, main loop, inversion, polish, leader Bland, refactor;
+                                  // [6] main-loop calls, [7] polish calls
 
     GM_DEV void trace_pivot(int enter_var, int leave_var) {  // called by ONE thread, before the counters move
         if constexpr (WARM) {
@@ -1869,12 +1881,16 @@ struct SolverT {
     // =================================================================================================
     static constexpr int CNB = 32;          // inversion panel width (a multiple of the 8-wide DMMA tile)
     enum { CMD_EXIT = 0, CMD_MAIN = 1, CMD_INVERT = 2 };
-    enum { CR_OPT = 0, CR_UNBOUNDED = 1, CR_BLAND = 2, CR_REFACTOR = 3, CR_ITER = 4 };
+    enum { CR_OPT = 0, CR_UNBOUNDED = 1, CR_BLAND = 2, CR_REFACTOR = 3, CR_ITER = 4, CR_BLAND_FAIL = 5 };
     // mailbox layout (doubles): [0] command, [1..9] arguments, [10] flag; then per-CTA records
     static constexpr int MAIL_HDR = 16;
     GM_DEV double* rec_a(int g) const { return mail + MAIL_HDR + 2 * g; }           // {value, position}
     GM_DEV double* rec_b(int g) const { return mail + MAIL_HDR + 2 * G + 4 * g; }   // {ratio, row, alpha, buffer bit}
     GM_DEV double* rec_n(int g) const { return mail + MAIL_HDR + 6 * G + 2 * g; }   // {inf-norm part, 1-norm part}
+    GM_DEV double* rec_c(int g) const { return mail + MAIL_HDR + 8 * G + 4 * g; }   // Bland: {row, alpha, ratio, bit}
+    GM_DEV void prof_add(int k, long long t0) {
+        if (gm_tid() == 0) prof_t[k] += gm_clock() - t0;
+    }
 
     // Group barrier: every CTA of the group arrives, all earlier global writes of the group are visible afterwards.
     GM_DEV void grp_sync() {
@@ -1947,18 +1963,23 @@ struct SolverT {
             const bool wr = pending && (is_l || f != 0.0);
             const double* src = bi_buf(bit) + (size_t)i * ldb;
             double* dst = bi_buf(bit ^ 1) + (size_t)i * ldb;
-            double a0 = 0, a1 = 0;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             int j = j0 + lane;
-            for (; j + 32 < j1; j += 64) {
-                double v0 = src[j], v1 = src[j + 32];
+            for (; j + 96 < j1; j += 128) {  // four strips per trip, the loads issued before anything depends on them
+                double v0 = src[j], v1 = src[j + 32], v2 = src[j + 64], v3 = src[j + 96];
                 if (wr) {
-                    v0 = is_l ? s_prow[j] : v0 - f * s_prow[j];
-                    v1 = is_l ? s_prow[j + 32] : v1 - f * s_prow[j + 32];
-                    dst[j] = v0; dst[j + 32] = v1;
+                    const double p0 = s_prow[j], p1 = s_prow[j + 32], p2 = s_prow[j + 64], p3 = s_prow[j + 96];
+                    v0 = is_l ? p0 : v0 - f * p0;
+                    v1 = is_l ? p1 : v1 - f * p1;
+                    v2 = is_l ? p2 : v2 - f * p2;
+                    v3 = is_l ? p3 : v3 - f * p3;
+                    dst[j] = v0; dst[j + 32] = v1; dst[j + 64] = v2; dst[j + 96] = v3;
                 }
-                if (with_dot) { a0 += v0 * s_ae[j]; a1 += v1 * s_ae[j + 32]; }
+                if (with_dot) {
+                    a0 += v0 * s_ae[j]; a1 += v1 * s_ae[j + 32]; a2 += v2 * s_ae[j + 64]; a3 += v3 * s_ae[j + 96];
+                }
             }
-            if (j < j1) {
+            for (; j < j1; j += 32) {
                 double v0 = src[j];
                 if (wr) {
                     v0 = is_l ? s_prow[j] : v0 - f * s_prow[j];
@@ -1967,7 +1988,7 @@ struct SolverT {
                 if (with_dot) a0 += v0 * s_ae[j];
             }
             if (with_dot) {
-                double acc = a0 + a1;
+                double acc = (a0 + a1) + (a2 + a3);
                 for (int d = 16; d >= 1; d >>= 1) acc += gm_shfl_xor(acc, d);
                 if (lane == 0) s_part[pr] = acc;
             }
@@ -2028,10 +2049,10 @@ struct SolverT {
             const double bestv = best.v;
             const int besti = bestv == bestv ? (int)rec_a(best.i)[1] : -1;
             if (besti < 0 || bestv >= -tol || (!fresh && bestv > -1e-9 * cscale)) { reason = CR_OPT; break; }
-            const int e = besti;
-            const double re = bestv;
+            const int e_price = besti;
+            const double re_price = bestv;
             // ---- entering column, then my rows: pending update + FTRAN + ratio test (:306-342, :268)
-            for (int i = t; i < m; i += T) s_ae[i] = W[(size_t)i * ldw + m + e];
+            for (int i = t; i < m; i += T) s_ae[i] = W[(size_t)i * ldw + m + e_price];
             gm_sync();
             coop_rows_pass(r0, nr, pending, lprev, true);
             pending = false;
@@ -2052,12 +2073,74 @@ struct SolverT {
             MinLoc bl = block_argmin(G, [&](int g) { return rec_b(g)[1] >= 0.0 ? rec_b(g)[0] : NAN; });
             const double mvv = bl.v == bl.v ? bl.v : INFINITY;
             if (mvv == INFINITY) { reason = CR_UNBOUNDED; break; }  // Min(d) >= 0 (:329-331)
-            if (mvv <= 0.0) { reason = CR_BLAND; e_out = e; break; }  // :268-277, decided by the leader
-            const int l = (int)rec_b(bl.i)[1];
-            const double alpha_l = rec_b(bl.i)[2];
-            const int bit_l = (int)rec_b(bl.i)[3];
+            int l = (int)rec_b(bl.i)[1];
+            double alpha_l = rec_b(bl.i)[2], theta = mvv;
+            int bit_l = (int)rec_b(bl.i)[3];
+            int e = e_price;
+            double re = re_price;
+            bool bland = false;
+            if (mvv <= 0.0) {
+                // ---- replaceBland (:347-383) by the whole group: candidates in list order, each with its own FTRAN
+                // over the row blocks. The step-size test is exact; a zero-step leaving position is accepted here
+                // only when its pivot element is healthy (|alpha_p| > 1e-6 max|alpha|, which puts the swapped
+                // basis' condition number far below the reference's 1e16 bound); a weaker pivot element hands the
+                // decision to the leader, which evaluates the exact condition number (replace_bland).
+                nbland++;
+                bland = true;
+                int from = 0, verdict = -1;  // -1 searching, 0 accepted, else CR_*
+                while (verdict < 0) {
+                    const int i = block_min_int(nn - from, [&](int q) { return r[from + q] <= -GM_BLAND_NEG_TOL ? from + q : INT_MAX; });
+                    if (i == INT_MAX) { verdict = CR_BLAND_FAIL; break; }
+                    for (int q = t; q < m; q += T) s_ae[q] = W[(size_t)q * ldw + m + i];
+                    gm_sync();
+                    coop_rows_pass(r0, nr, false, -1, true);
+                    auto ratio = [&](int q) {
+                        double d = -s_al[q];
+                        if (fabs(d) < GM_D_ROUND_TOL) d = 0.0;
+                        return d < 0.0 ? s_xb[q] / fabs(d) : INFINITY;
+                    };
+                    MinLoc m2 = block_argmin(nr, ratio);
+                    const double dm = block_max(nr, [&](int q) { return fabs(s_al[q]); });
+                    const int pany = block_min_int(nr, [&](int q) { return ratio(q) <= GM_BLAND_ZERO_TOL ? q : INT_MAX; });
+                    if (t == 0) {
+                        double* rb = rec_b(rank);
+                        const bool valid = nr > 0 && m2.v == m2.v;
+                        rb[0] = valid ? m2.v : INFINITY;
+                        rb[1] = valid ? (double)(r0 + m2.i) : -1.0;
+                        rb[2] = valid ? s_al[m2.i] : 0.0;
+                        rb[3] = valid ? (double)s_bit[m2.i] : 0.0;
+                        rec_n(rank)[0] = dm;
+                        double* rc = rec_c(rank);
+                        rc[0] = pany != INT_MAX ? (double)(r0 + pany) : -1.0;
+                        rc[1] = pany != INT_MAX ? s_al[pany] : 0.0;
+                        rc[2] = pany != INT_MAX ? ratio(pany) : 0.0;
+                        rc[3] = pany != INT_MAX ? (double)s_bit[pany] : 0.0;
+                    }
+                    grp_sync();
+                    MinLoc b2 = block_argmin(G, [&](int g) { return rec_b(g)[1] >= 0.0 ? rec_b(g)[0] : NAN; });
+                    const double mv2 = b2.v == b2.v ? b2.v : INFINITY;
+                    const double dmax = block_max(G, [&](int g) { return rec_n(g)[0]; });
+                    const int gp = block_min_int(G, [&](int g) { return rec_c(g)[0] >= 0.0 ? g : INT_MAX; });
+                    if (mv2 == INFINITY) { verdict = CR_UNBOUNDED; }
+                    else if (fabs(mv2) > GM_BLAND_ZERO_TOL) {
+                        l = (int)rec_b(b2.i)[1]; alpha_l = rec_b(b2.i)[2]; bit_l = (int)rec_b(b2.i)[3]; theta = mv2;
+                        e = i; verdict = 0;
+                    } else if (gp != INT_MAX && fabs(rec_c(gp)[1]) > 1e-6 * dmax) {
+                        l = (int)rec_c(gp)[0]; alpha_l = rec_c(gp)[1]; theta = rec_c(gp)[2]; bit_l = (int)rec_c(gp)[3];
+                        e = i; verdict = 0;
+                    } else if (gp != INT_MAX) {
+                        verdict = CR_BLAND;  // weak pivot element: the exact condition test decides (leader)
+                    } else {
+                        from = i + 1;
+                        if (from >= nn) verdict = CR_BLAND_FAIL;
+                    }
+                    grp_sync();  // the records are rewritten by the next candidate / the next pivot
+                }
+                if (verdict != 0) { reason = verdict; e_out = e_price; nbland -= (verdict == CR_BLAND); break; }
+                re = r[e];
+            }
             // ---- basis change (:280-292)
-            const double inv = 1.0 / alpha_l, theta = mvv;
+            const double inv = 1.0 / alpha_l;
             {
                 const double* prw = bi_buf(bit_l) + (size_t)l * ldb;
                 for (int j = t; j < m; j += T) s_prow[j] = prw[j] * inv;
@@ -2075,7 +2158,7 @@ struct SolverT {
             }
             if (rank == 0 && t == 0) {
                 const int v = basic[l];
-                cur_phase = phase; cur_bland = 0;
+                cur_phase = phase; cur_bland = bland ? 1 : 0;
                 trace_pivot(nonbasic[e], v);
                 basic[l] = nonbasic[e];
                 nonbasic[e] = v;
@@ -2119,14 +2202,21 @@ struct SolverT {
                 mail[0] = CMD_MAIN; mail[1] = tol; mail[2] = phase; mail[3] = fresh ? 1.0 : 0.0; mail[4] = since;
                 mail[5] = piv1; mail[6] = piv2; mail[7] = cscale; mail[8] = nn; mail[9] = ncols;
             }
+            long long t0 = gm_clock();
             grp_sync();
             int e = 0;
             const int reason = coop_loop(tol, phase, fresh, since, e);
+            prof_add(1, t0);
+            if (t == 0) prof_t[6]++;
             if (reason == CR_ITER) return GM_ERR_ITERATION_LIMIT;
             if (reason == CR_UNBOUNDED) return GM_ERR_UNBOUNDED;
+            if (reason == CR_BLAND_FAIL) return GM_ERR_BLAND;
             if (reason == CR_OPT) {
                 if (!fresh) {  // confirm optimality with fresh-quality xb and y, like the other tiers
+                    t0 = gm_clock();
                     const int rc = polish();
+                    prof_add(3, t0);
+                    if (t == 0) prof_t[7]++;
                     if (rc != GM_OK) return rc;
                     fresh = true;
                     continue;
@@ -2134,13 +2224,17 @@ struct SolverT {
                 return GM_OK;
             }
             if (reason == CR_REFACTOR) {
+                t0 = gm_clock();
                 const int rc = refactor();
+                prof_add(5, t0);
                 if (rc != GM_OK) return rc;
                 fresh = true;
                 since = 0;
                 continue;
             }
-            // CR_BLAND: the degenerate step is resolved by the leader alone on the state in HBM (:268-277)
+            // CR_BLAND with a weak pivot element: resolved by the leader alone on the state in HBM, with the exact
+            // condition test of replace_bland (:268-277, :369-379)
+            t0 = gm_clock();
             nbland++;
             int l = 0;
             bool weak;
@@ -2159,6 +2253,7 @@ struct SolverT {
                 fresh = true;
                 since = 0;
             }
+            prof_add(4, t0);
         }
     }
 
@@ -2182,40 +2277,48 @@ struct SolverT {
         double anorm_inf, anorm_1, inorm_inf, inorm_1;
         coop_norms(M, r0, nr, anorm_inf, anorm_1);
         int singular = 0;
-        for (int kb = 0; kb < m; kb += CNB) {
-            const int nbk = m - kb < CNB ? m - kb : CNB;
+        const int NBW = s_pan ? 16 : CNB;          // panel width
+        const int pld = s_pan ? 17 : CNB;          // row stride of the working panel (padded in shared memory)
+        double* pan = s_pan ? s_pan : Tp;
+        double* pcol = s_pan ? s_pan + (size_t)m * 17 : t1;      // the eliminated column
+        double* prw = s_pan ? pcol + ((m + 3) & ~3) : prow;     // the scaled pivot row of the panel
+        for (int kb = 0; kb < m; kb += NBW) {
+            const int nbk = m - kb < NBW ? m - kb : NBW;
             if (rank == 0) {
-                for_each_2d(m, nbk, [&](int i, int q) { Tp[(size_t)i * CNB + q] = M[(size_t)i * ldb + kb + q]; });
+                for_each_2d(m, nbk, [&](int i, int q) { pan[(size_t)i * pld + q] = M[(size_t)i * ldb + kb + q]; });
                 gm_sync();
                 for (int q = 0; q < nbk && !singular; ++q) {
                     const int k = kb + q;
-                    MinLoc pl = block_argmin(m - k, [&](int s2) { return -fabs(Tp[(size_t)(k + s2) * CNB + q]); });
+                    MinLoc pl = block_argmin(m - k, [&](int s2) { return -fabs(pan[(size_t)(k + s2) * pld + q]); });
                     const int p = k + pl.i;
                     const double pabs = -pl.v;
                     if (!(pabs > 0.0) || pabs == INFINITY) { singular = 1; break; }
                     if (p != k) {
                         for (int qq = t; qq < nbk; qq += T) {
-                            const double a = Tp[(size_t)k * CNB + qq];
-                            Tp[(size_t)k * CNB + qq] = Tp[(size_t)p * CNB + qq];
-                            Tp[(size_t)p * CNB + qq] = a;
+                            const double a = pan[(size_t)k * pld + qq];
+                            pan[(size_t)k * pld + qq] = pan[(size_t)p * pld + qq];
+                            pan[(size_t)p * pld + qq] = a;
                         }
                     }
                     if (t == 0) ipiv[k] = p;
                     gm_sync();
-                    const double pv = Tp[(size_t)k * CNB + q];
-                    for (int i = t; i < m; i += T) t1[i] = Tp[(size_t)i * CNB + q];
-                    for (int qq = t; qq < nbk; qq += T) prow[qq] = (qq == q ? 1.0 : Tp[(size_t)k * CNB + qq]) / pv;
+                    const double pv = pan[(size_t)k * pld + q];
+                    for (int i = t; i < m; i += T) pcol[i] = pan[(size_t)i * pld + q];
+                    for (int qq = t; qq < nbk; qq += T) prw[qq] = (qq == q ? 1.0 : pan[(size_t)k * pld + qq]) / pv;
                     gm_sync();
                     for_each_2d(m, nbk, [&](int i, int qq) {
-                        const double base = qq == q ? 0.0 : Tp[(size_t)i * CNB + qq];
-                        Tp[(size_t)i * CNB + qq] = i == k ? prow[qq] : base - t1[i] * prow[qq];
+                        const double base = qq == q ? 0.0 : pan[(size_t)i * pld + qq];
+                        pan[(size_t)i * pld + qq] = i == k ? prw[qq] : base - pcol[i] * prw[qq];
                     });
                     gm_sync();
                 }
                 if (!singular) {
-                    for_each_2d(m, nbk, [&](int i, int q) { M[(size_t)i * ldb + kb + q] = Tp[(size_t)i * CNB + q]; });
-                    gm_sync();
-                    for (int q = t; q < nbk; q += T) Tp[(size_t)(kb + q) * CNB + q] -= 1.0;
+                    // the panel's columns are final; Tp (HBM, row stride NBW) gets T[:, K] - I for the trailing update
+                    for_each_2d(m, nbk, [&](int i, int q) {
+                        const double v = pan[(size_t)i * pld + q];
+                        M[(size_t)i * ldb + kb + q] = v;
+                        Tp[(size_t)i * NBW + q] = i == kb + q ? v - 1.0 : v;
+                    });
                 }
                 if (t == 0) mail[10] = singular;
             }
@@ -2247,7 +2350,7 @@ struct SolverT {
 #pragma unroll
                     for (int kk = 0; kk < CNB / 4; ++kk) {
                         const int q = kk * 4 + acol;
-                        afr[kk] = (i < m && q < nbk) ? Tp[(size_t)i * CNB + q] : 0.0;
+                        afr[kk] = (i < m && q < nbk) ? Tp[(size_t)i * NBW + q] : 0.0;
                     }
                     for (int jt = warp; jt < ntile; jt += nw) {
                         const int j0 = jt * 8;
@@ -2258,9 +2361,11 @@ struct SolverT {
                         const int jb = j0 + arow;
 #pragma unroll
                         for (int kk = 0; kk < CNB / 4; ++kk) {
-                            const int q = kk * 4 + acol;
-                            const double bfr = (q < nbk && jb < m) ? Rs[(size_t)q * ldb + jb] : 0.0;
-                            gm_dmma_8x8x4(c0v, c1v, afr[kk], bfr);
+                            if (kk * 4 < nbk) {  // warp-uniform: panels narrower than CNB stop early
+                                const int q = kk * 4 + acol;
+                                const double bfr = (q < nbk && jb < m) ? Rs[(size_t)q * ldb + jb] : 0.0;
+                                gm_dmma_8x8x4(c0v, c1v, afr[kk], bfr);
+                            }
                         }
                         if (i < m && jc < m) M[(size_t)i * ldb + jc] = c0v;
                         if (i < m && jc + 1 < m) M[(size_t)i * ldb + jc + 1] = c1v;
@@ -2328,8 +2433,11 @@ struct SolverT {
 
     GM_DEV int invert_basis_coop(double* cond1) {
         if (gm_tid() == 0) mail[0] = CMD_INVERT;
+        const long long t0 = gm_clock();
         grp_sync();
-        return coop_invert_body(cond1);
+        const int rc = coop_invert_body(cond1);
+        prof_add(2, t0);
+        return rc;
     }
 
     // Helpers: execute what the leader posts until it says CMD_EXIT.
@@ -2669,7 +2777,7 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
     const int grp = gm_block_id() / G;
     const int m = P.m0 + P.L, n = P.n0 + P.L;
     const WsLayout w = ws_layout(m, n, T, false, true);
-    const CoopLayout c = coop_layout(m, n, T, G);
+    const CoopLayout c = coop_layout(m, n, T, G, P.coop_pan == 16 ? (size_t)1 << 30 : 0);
     double* base = P.work + (size_t)grp * P.work_stride;
     s.bind_workspace(P, base + w.W, base + w.Bi, base + w.big_doubles, nullptr, nullptr);
     s.G = G;
@@ -2680,6 +2788,8 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
     s.Bi1 = base + c.Bi1; s.Tp = base + c.Tp; s.Rs = base + c.Rs;
     s.s_y = smem + c.s_y; s.s_prow = smem + c.s_prow; s.s_ae = smem + c.s_ae; s.s_xb = smem + c.s_xb;
     s.s_al = smem + c.s_al; s.s_f = smem + c.s_f; s.s_r = smem + c.s_r; s.s_part = smem + c.s_part;
+    s.s_pan = P.coop_pan == 16 ? smem : nullptr;             // aliases the scratch above (see coop_layout)
+    for (int k = 0; k < 8; ++k) s.prof_t[k] = 0;
     s.red = smem + c.s_red;                                   // block reductions go through shared memory
     s.s_bit = reinterpret_cast<int*>(smem + c.s_bit);
     s.redi = reinterpret_cast<int*>(smem + c.s_redi);
@@ -2697,7 +2807,12 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
         if (item >= P.count) break;
         const int lp = P.lp_list ? P.lp_list[item] : item;
         s.bind_lp(P, lp);
+        for (int k = 0; k < 8; ++k) s.prof_t[k] = 0;
+        const long long t0 = gm_clock();
         s.solve(P, lp);
+        s.prof_add(0, t0);
+        if (P.prof && gm_tid() == 0)
+            for (int k = 0; k < 8; ++k) P.prof[(size_t)lp * 8 + k] = s.prof_t[k];
     }
     s.coop_post_exit();
 }

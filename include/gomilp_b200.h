@@ -61,6 +61,13 @@ typedef struct gm_options {
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
 
+/* Cooperative tier (6) only: arm before a host-buffer compute call; every LP of that call reports 8 int64: SM clock
+ * cycles its leader CTA spent in [0] the whole solve, [1] the cooperative main loop, [2] basis inversions, [3] polish
+ * (refinement, may nest an inversion), [4] leader-only Bland pivots, [5] periodic refactorisation, and the counts
+ * [6] main-loop entries, [7] polish calls. The per-wave device-timing extension of BnbMiddleware, one level down. */
+int gm_profile_arm(void);
+int64_t gm_profile_fetch(int64_t* out /* [lps][8] */, int64_t lps);
+
 /* Measured shared-memory bandwidth of the current device in GB/s (all SMs streaming conflict-free 16-byte loads):
  * the denominator of the roofline of the shared-memory resident tiers (bench.py). */
 int gm_microbench_smem_gbs(double* gbs_out);

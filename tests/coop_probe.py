@@ -22,10 +22,13 @@ def bpp(m, n):
 def run(label, c, A, b, **opt):
     gm.set_options(**opt)
     try:
+        gm.profile_arm()
         t0 = time.perf_counter()
         g = gm.simplex_batch(c, A, b, want_basis=False)
         wall = time.perf_counter() - t0
         tm = gm.last_timing()
+        prof = gm.profile_fetch(1)
+        pr = prof[0].astype(float) if len(prof) else None
         piv = int(g["pivots"].sum())
         m, n = A.shape[1:]
         s = g["stats"] if "stats" in g else None
@@ -34,7 +37,12 @@ def run(label, c, A, b, **opt):
                           "us_per_pivot_round": 1e3 * tm["kernel_ms"] / max(1, piv / A.shape[0]),
                           "alg_GBps": piv * bpp(m, n) / (tm["kernel_ms"] * 1e-3) / 1e9, "wall_s": wall,
                           "inversions": None if s is None else int(s[:, 3].sum()),
-                          "bland": None if s is None else int(s[:, 2].sum())}), flush=True)
+                          "bland": None if s is None else int(s[:, 2].sum()),
+                          "leader_cycles_pct": None if pr is None or pr[0] == 0 else {
+                              "main_loop": round(100 * pr[1] / pr[0], 1), "inversion": round(100 * pr[2] / pr[0], 1),
+                              "polish": round(100 * pr[3] / pr[0], 1), "leader_bland": round(100 * pr[4] / pr[0], 1),
+                              "refactor": round(100 * pr[5] / pr[0], 1), "entries": int(pr[6]), "polishes": int(pr[7]),
+                              "solve_Mcyc": round(pr[0] / 1e6, 1)}}), flush=True)
         return g
     finally:
         gm.set_options()
@@ -79,3 +87,16 @@ print(json.dumps({"case": "C3 depth-1 wave (2 nodes)", "tier": tm["tier"], "grid
                   "z": w.z.tolist(), "pivots": (w.stats[:, 0] + w.stats[:, 1]).tolist(), "bland": w.stats[:, 2].tolist(),
                   "kernel_ms": tm["kernel_ms"], "wall_s": time.perf_counter() - t0}), flush=True)
 gm.free_root(root)
+
+# which B&B workloads run through without a solver-failure panic (reference semantics, tree.go:272)
+from gomilp_b200 import status as S  # noqa: E402
+for label, prob, lim in (("c5 n=50", c5_general_integer(50), 4095), ("c5 n=100", c5_general_integer(100), 2047),
+                         ("c5 n=200", c5_general_integer(200), 511), ("knapsack 60x10", knapsack(np.random.default_rng(7), 60, 10), 4095),
+                         ("knapsack 120x40", knapsack(np.random.default_rng(7), 120, 40), 1023),
+                         ("knapsack 500x200 (C3)", knapsack(np.random.default_rng(7), 500, 200), 63)):
+    t0 = time.perf_counter()
+    r = gm.milp_solve(prob["c"], None, None, prob["G"], prob["h"], prob["integrality"], mode=S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN,
+                      heuristic=1, node_limit=lim, keep_log=False)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"case": "bnb " + label, "budget": lim, "status": r.status, "lp_status": r.lp_status, "nodes": r.nodes,
+                      "waves": r.waves, "pivots": r.pivots, "wall_s": dt, "nodes_per_sec": r.nodes / dt}), flush=True)

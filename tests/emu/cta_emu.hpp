@@ -278,6 +278,7 @@ inline double gm_ldg(const double* p) { return *p; }
 inline int gm_block_id() { return emu::current()->cur / emu::current()->T; }
 inline void gm_threadfence() {}
 inline void gm_spin_pause() { emu::yield_as(emu::RUN); }
+inline long long gm_clock() { return 0; }
 inline void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 inline unsigned long long gm_ld_acquire_u64(const unsigned long long* p) { return *(volatile const unsigned long long*)p; }
 // D(8x8) = A(8x4) * B(4x8) + C with the m8n8k4 fragment layout of mma.sync (see cta_rt.cuh)

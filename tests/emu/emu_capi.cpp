@@ -7,6 +7,7 @@
 #include "../../gomilp_b200/csrc/simplex_cta.cuh"
 
 static const int* g_emu_lp_list = nullptr;
+static int g_emu_coop_pan = 1;  // 0: force the inversion panel of the cooperative tier into (emulated) HBM
 static int g_emu_quad = 0;  // 1: run the generic solver as tier 2 (quad-mapped main loop)  // retry launches: work item k solves LP list[k]
 
 extern "C" {
@@ -103,7 +104,8 @@ int emu_coop_batch(int count, const double* c, const double* A, const double* b,
     P.tier = 6;
     P.coop_G = G;
     if (T % 32 != 0 || G < 1 || groups < 1) return -2;
-    const gm::CoopLayout cl = gm::coop_layout(m0 + L, n0 + L, T, G);
+    const gm::CoopLayout cl = gm::coop_layout(m0 + L, n0 + L, T, G, g_emu_coop_pan ? (size_t)200 * 1024 : 0);
+    P.coop_pan = cl.pan_nb;
     std::vector<double> work((size_t)groups * cl.group_doubles + 16, 0.0);
     std::vector<unsigned long long> bars(groups, 0ull);
     P.work = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(work.data()) + 31) & ~uintptr_t(31));
@@ -149,6 +151,7 @@ int g_reg = 0;
 extern "C" {
 void emu_set_threads(int T, int reg) { g_T = T; g_reg = reg; }
 void emu_set_quad(int on) { g_emu_quad = on; }
+void emu_set_coop_pan(int on) { g_emu_coop_pan = on; }
 int gm_upload_root(const double* c0, const double* A0, int64_t lda, const double* b0, int64_t m0, int64_t n0,
                    gm_root_t* out) {
     EmuRoot r;

@@ -34,6 +34,17 @@ def report(line: str):
         pass
 
 
+def logs_equal(a, b) -> bool:
+    """Decision logs row by row; NaN objectives (infeasible nodes) compare equal to NaN."""
+    if len(a) != len(b):
+        return False
+    for ra, rb in zip(a, b):
+        for va, vb in zip(ra, rb):
+            if va != vb and not (isinstance(va, float) and isinstance(vb, float) and va != va and vb != vb):
+                return False
+    return True
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
@@ -49,7 +60,7 @@ def _wave_fixture_check(name, c0, A0, b0, expect_tier=None, force_tier=0, only_d
     m0, n0 = A0.shape
     root = gm.upload_root(c0, A0, b0)
     worst_z = worst_x = 0.0
-    same_piv = total = bland_nodes = bland_fired = repair_nodes = repair_fired = 0
+    same_piv = total = bland_nodes = bland_fired = repair_nodes = repair_fired = ref_failed = 0
     tiers = set()
     t_dev = 0.0
     try:
@@ -67,6 +78,17 @@ def _wave_fixture_check(name, c0, A0, b0, expect_tier=None, force_tier=0, only_d
             t_dev += tm["kernel_ms"]
             for q, k in enumerate(idx):
                 total += 1
+                if int(z["status"][k]) == S.GM_ERR_CONDITION:
+                    # The reference's own arithmetic gives up on this node (mat.Condition from a fresh LU of a basis
+                    # reached through zero-step Bland pivots; GoMILP would panic, tree.go:272). Nothing to replay:
+                    # the engine must still return the true optimum, checked against HiGHS.
+                    from scipy.optimize import linprog
+                    cc, AA, bb = node_lp(c0, A0, b0, bvar[q], z["bsign"][k, :L], z["brhs"][k, :L])
+                    hs = linprog(cc, A_eq=AA, b_eq=bb, bounds=(0, None), method="highs")
+                    ref_failed += 1
+                    assert w.status[q] == S.GM_OK and hs.status == 0, (name, L, q, w.status[q], hs.status)
+                    assert abs(w.z[q] - hs.fun) <= 1e-7 * max(1.0, abs(hs.fun)), (w.z[q], hs.fun)
+                    continue
                 assert w.status[q] == int(z["status"][k]), (name, L, q, w.status[q], int(z["status"][k]))
                 if int(z["status"][k]) == S.GM_OK:
                     worst_z = max(worst_z, rel(w.z[q], z["z"][k]))
@@ -82,7 +104,8 @@ def _wave_fixture_check(name, c0, A0, b0, expect_tier=None, force_tier=0, only_d
         gm.free_root(root)
     report(f"{name} ({m0}x{n0}+L) tier {sorted(tiers)}: {total} node LPs, status equal, max rel err z {worst_z:.2e} "
            f"x {worst_x:.2e}; same pivot count {same_piv}/{total}; Bland fired on {bland_fired}/{bland_nodes} nodes "
-           f"where the oracle's did, repair loop {repair_fired}/{repair_nodes}; device {t_dev:.1f} ms")
+           f"where the oracle's did, repair loop {repair_fired}/{repair_nodes}; {ref_failed} nodes where the reference "
+           f"arithmetic aborts with mat.Condition solved and checked against HiGHS; device {t_dev:.1f} ms")
     assert worst_z <= RTOL and worst_x <= RTOL
     if expect_tier is not None:
         assert expect_tier in tiers
@@ -118,11 +141,19 @@ def test_c4_single_large_lp():
     assert str(z["A_sha"]) == sha(A), "generator drift: regenerate the fixture"
     cap = int(z["cold_cap"])
     gm.trace_arm(0, 4096)
+    gm.profile_arm()
     t0 = time.perf_counter()
     r = gm.simplex(c, A, b)
     wall = time.perf_counter() - t0
     tm = gm.last_timing()
     tr = gm.trace_fetch(4096)
+    prof = gm.profile_fetch(1)
+    if len(prof):
+        pr = prof[0].astype(float)
+        report("c4 leader cycles: solve %.0f Mcyc = main loop %.1f%% (%d entries) + inversion %.1f%% + polish %.1f%% (%d calls) "
+               "+ leader Bland %.1f%% + refactor %.1f%% (overlapping categories: refactor and polish contain inversions)"
+               % (pr[0] / 1e6, 100 * pr[1] / pr[0], int(pr[6]), 100 * pr[2] / pr[0], 100 * pr[3] / pr[0], int(pr[7]),
+                  100 * pr[4] / pr[0], 100 * pr[5] / pr[0]))
     assert tm["tier"] == 6 and tm["grid"] >= 128
     assert r.status == S.GM_OK
     ez, ex = rel(r.optF, z["z"]), rel(r.x, z["x"])
@@ -212,7 +243,7 @@ def test_c1_milps_decision_logs_under_equal_budgets():
             dv = gm.milp_solve(*args, heuristic=1, mode=mode | S.GM_BNB_DEVICE_SCAN, node_limit=budget)
             # the two schedulers of this repo see the same LP results: they must agree exactly
             assert (dv.status, dv.lp_status, dv.nodes, dv.pivots) == (g.status, g.lp_status, g.nodes, g.pivots), k
-            assert dv.log == g.log, k
+            assert logs_equal(dv.log, g.log), k
             if g.x is not None:
                 assert np.array_equal(dv.x, g.x) and dv.z == g.z
             pre = f"p{k}_m{mode}_"
@@ -263,7 +294,7 @@ def test_device_scan_equals_host_replay_on_knapsack():
         d = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
                           mode=S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN, heuristic=heur, node_limit=lim)
         assert (a.status, a.lp_status, a.nodes, a.waves, a.pivots) == (d.status, d.lp_status, d.nodes, d.waves, d.pivots)
-        assert a.log == d.log
+        assert logs_equal(a.log, d.log)
         if a.x is not None:
             assert np.array_equal(a.x, d.x) and a.z == d.z
 

@@ -104,11 +104,15 @@ def test_every_tier_matches_oracle():
     rng = np.random.default_rng(5)
     c, A, b = feasible_bounded_lp(rng, 150, 260, 6)
     g = gm.simplex_batch(c, A, b)
-    assert gm.last_timing()["tier"] == 3
+    assert gm.last_timing()["tier"] == 6   # 6 LPs on 148 SMs: the cooperative tier, 24 CTAs per LP
     o = oracle.simplex_batch(c, A, b, threads=oracle.num_hw_threads())
     assert (g["status"] == o["status"]).all()
     assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
     try:
+        gm.set_options(force_tier=3)                     # basis inverse in shared memory, W in HBM, one CTA per LP
+        g3 = gm.simplex_batch(c, A, b)
+        assert gm.last_timing()["tier"] == 3
+        assert (g3["status"] == o["status"]).all() and _close(g3["x"], o["x"]) and (g3["pivots"] == g["pivots"]).all()
         gm.set_options(force_tier=4)                     # W and Bi in HBM (m < 384: plain loads)
         g2 = gm.simplex_batch(c, A, b)
         assert (g2["status"] == o["status"]).all() and _close(g2["x"], o["x"])
@@ -124,17 +128,24 @@ def test_every_tier_matches_oracle():
     b4 = 1.0 + rng.random((2, m4))
     c4 = np.zeros((2, n4))
     c4[:, : n4 - m4] = -rng.random((2, n4 - m4))
-    g4 = gm.simplex_batch(c4, A4, b4)
+    try:
+        gm.set_options(force_tier=4)
+        g4 = gm.simplex_batch(c4, A4, b4)
+    finally:
+        gm.set_options()
     assert gm.last_timing()["tier"] == 4 and (g4["status"] == S.GM_OK).all()
     assert np.abs(np.einsum("kij,kj->ki", A4, g4["x"]) - b4).max() < 1e-9 and g4["x"].min() >= -1e-12
     for k in range(2):
         hs = linprog(c4[k], A_eq=A4[k], b_eq=b4[k], bounds=(0, None), method="highs")
         assert hs.status == 0 and abs(hs.fun - g4["optF"][k]) <= 1e-7 * max(1.0, abs(hs.fun))
     try:
-        gm.set_options(no_tma_ring=True)
+        gm.set_options(no_tma_ring=True, force_tier=4)
         g5 = gm.simplex_batch(c4, A4, b4)
     finally:
         gm.set_options()
+    g6 = gm.simplex_batch(c4, A4, b4)                    # the shape's own choice: cooperative, 74 CTAs per LP
+    assert gm.last_timing()["tier"] == 6 and (g6["status"] == S.GM_OK).all()
+    assert _close(g6["optF"], g4["optF"]) and _close(g6["x"], g4["x"], 1e-7) and (g6["pivots"] == g4["pivots"]).all()
     assert (g5["status"] == S.GM_OK).all() and _close(g5["optF"], g4["optF"]) and _close(g5["x"], g4["x"], 1e-7)
     assert (g5["pivots"] == g4["pivots"]).all()
     c, A, b = feasible_bounded_lp(rng, 16, 40, 32)
@@ -142,8 +153,8 @@ def test_every_tier_matches_oracle():
     o = oracle.simplex_batch(c, A, b)
     o2 = oracle.simplex_batch(c2, A2, b2, max_pivots=20000)
     try:
-        for tier in (1, 2, 3, 4, 5):
-            gm.set_options(force_tier=tier)
+        for tier in (1, 2, 3, 4, 5, 6):
+            gm.set_options(force_tier=tier, coop_group=4 if tier == 6 else 0)
             g = gm.simplex_batch(c, A, b)
             assert gm.last_timing()["tier"] == tier
             assert (g["status"] == o["status"]).all() and _close(g["x"], o["x"]) and _close(g["optF"], o["optF"])
