@@ -180,8 +180,16 @@ def bnb_extra(gm):
                         "host_replay": row(*best_of(p, 1, 8192)), "device_scan": row(*best_of(p, 1 | 8, 8192)),
                         "warm_start_host_replay": row(*best_of(p, 1 | 4, 8192))}
         p3 = knapsack(np.random.default_rng(7), 500, 200)
-        out["c3"] = {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, node "
-                                 "budget 255, device-side scan, cold children", **row(*best_of(p3, 1 | 8, 255, reps=1))}
+        r3, dt3 = best_of(p3, 1 | 8, 7, reps=1)
+        out["c3"] = {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, first 7 "
+                                 "nodes (3 waves), device-side scan, cold children; deeper nodes of this instance are "
+                                 "degenerate enough that the reference's own arithmetic aborts (mat.Condition, "
+                                 "tests/golden/c3_knapsack.npz), so the budget stops before them", **row(r3, dt3),
+                     "lp_status": r3.lp_status}
+        from problems import c5_general_integer
+        p5 = c5_general_integer(200)
+        out["c5_n200"] = {"workload": "C5: general-integer MILP n=200 (300x500 + depth), FIXED most-infeasible, node budget "
+                                      "511, device-side scan, cold children", **row(*best_of(p5, 1 | 8, 511, reps=2))}
     except Exception as e:  # never let the extra break the contract line
         out["error"] = repr(e)
     return out
@@ -199,7 +207,8 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
                 uid = torch.frombuffer(bytearray(gm.capi.comm_unique_id()), dtype=torch.uint8).to(dev)
             dist.broadcast(uid, 0)
             gm.capi.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        p = knapsack(np.random.default_rng(7), 120, 40)   # 160 x 280 + depth: wide waves of HBM-tier LPs
+        from problems import c5_general_integer
+        p = c5_general_integer(100)   # C5, n = 100: 150 x 250 + depth, wide waves of 2048 node LPs
         limit = 4095
         best = None
         for rep in range(3):
@@ -217,8 +226,8 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if world > 1:
             gm.capi.comm_destroy()
-        return {"workload": "0-1 knapsack n=120 m=40 seed 7 (160x280 + depth), FIXED most-infeasible, node budget 4095, "
-                            "device-side scan, FIFO blocks per rank, best of 2 after a warm-up run",
+        return {"workload": "C5 general-integer MILP n=100 (150x250 + depth, bounds as rows), FIXED most-infeasible, node "
+                            "budget 4095, device-side scan, FIFO blocks per rank, cold children, best of 2 after a warm-up run",
                 "gpus": world, "nodes": r.nodes, "waves": r.waves, "pivots": r.pivots, "status": r.status,
                 "wall_s_max_over_ranks": float(t[0]), "nodes_per_sec": r.nodes / float(t[0]), "device_ms": r.device_ms,
                 "collective": "ncclAllGather of 32-byte node records, once per wave" if world > 1 else "none"}

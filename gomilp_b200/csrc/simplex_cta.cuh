@@ -230,6 +230,7 @@ struct SolverT {
     int wrows, vlen;  // rows of W incl. zero padding; length of the m-vectors incl. zero padding
     double cscale;   // max |cost| of the current phase: reduced costs below 1e-9 * cscale in magnitude are noise
     double anorm_w;  // norm of the basis at its last inversion, scale of the polish residual test
+    double cond_inf_last;  // ||B||_inf ||B^-1||_inf of the last successful inversion
     // HBM tier: ring of shared-memory stages fed by TMA bulk copies (nullptr: plain loads)
     double* ring;
     unsigned long long* ring_bar;
@@ -777,6 +778,7 @@ struct SolverT {
         *cond1 = anorm_1 * inorm_1;
         anorm_w = fmax(anorm_1, anorm_inf);
         const double cond_inf = anorm_inf * inorm_inf;
+        cond_inf_last = cond_inf;
         if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
         return 0;
     }
@@ -895,6 +897,7 @@ struct SolverT {
         *cond1 = anorm_1 * inorm_1;
         anorm_w = fmax(anorm_1, anorm_inf);
         const double cond_inf = anorm_inf * inorm_inf;
+        cond_inf_last = cond_inf;
         if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
         return 0;
     }
@@ -2404,6 +2407,7 @@ struct SolverT {
         if (cond1) *cond1 = anorm_1 * inorm_1;
         anorm_w = fmax(anorm_1, anorm_inf);
         const double cond_inf = anorm_inf * inorm_inf;
+        cond_inf_last = cond_inf;
         if (!(cond_inf <= GM_CONDITION_TOL)) return 1;
         return 0;
     }
@@ -2477,7 +2481,10 @@ struct SolverT {
             gm_sync();
             build_w(n, false);
             const int sing = invert_basis(&cond1);
-            have = !sing && cond1 * (double)m * (double)m <= GM_LINDEP_COND_TOL;
+            // Every m x k leading block M_k of these columns has cond_2(M_k) <= cond_2(B) (interlacing), the reference
+            // tests cond_1 of its k x k QR factor, cond_1(R_k) <= k cond_2(M_k), and cond_2(B)^2 <= cond_1(B) cond_inf(B):
+            // if m sqrt(cond_1 cond_inf) <= 1e12 the reverse scan provably accepts all m columns (:611-637).
+            have = !sing && (double)m * sqrt(cond1 * cond_inf_last) <= GM_LINDEP_COND_TOL;
         }
         if (!have) {
             const int k = scan_basis();
