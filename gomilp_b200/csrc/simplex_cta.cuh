@@ -1927,6 +1927,20 @@ struct SolverT {
             if (j < tw) {
                 const double* cp = M + c0 + j;
                 int i = rg;
+                // 16 independent loads per trip: an HBM-resident tile needs ~40 KB in flight per SM (B200: 6.5 TB/s x
+                // ~1 us / 148 SMs), i.e. more than the 8-byte loads of 512 threads can cover with a shallow unroll
+                for (; i + 15 * RG < nrows; i += 16 * RG) {
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v[u] = cp[(size_t)(i + u * RG) * ld];
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) {
+                        a0 += f(i + u * RG, v[u]);
+                        a1 += f(i + (u + 1) * RG, v[u + 1]);
+                        a2 += f(i + (u + 2) * RG, v[u + 2]);
+                        a3 += f(i + (u + 3) * RG, v[u + 3]);
+                    }
+                }
                 for (; i + 3 * RG < nrows; i += 4 * RG) {
                     const double v0 = cp[(size_t)i * ld], v1 = cp[(size_t)(i + RG) * ld];
                     const double v2 = cp[(size_t)(i + 2 * RG) * ld], v3 = cp[(size_t)(i + 3 * RG) * ld];
@@ -1967,22 +1981,44 @@ struct SolverT {
             const double* src = bi_buf(bit) + (size_t)i * ldb;
             double* dst = bi_buf(bit ^ 1) + (size_t)i * ldb;
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            int j = j0 + lane;
-            for (; j + 96 < j1; j += 128) {  // four strips per trip, the loads issued before anything depends on them
-                double v0 = src[j], v1 = src[j + 32], v2 = src[j + 64], v3 = src[j + 96];
+            // 16-byte loads, 8 strips of 64 columns per trip (128 B in flight per lane, 64 KB per CTA), all issued before
+            // anything depends on them: the HBM-resident case is bound by bytes in flight, not by arithmetic. Rows
+            // start 32-byte aligned (ldb is a multiple of 4) and chunks at multiples of 32 columns.
+            int j = j0 + 2 * lane;
+            for (; j + 448 + 1 < j1; j += 512) {
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2*>(src + j + 64 * u);
                 if (wr) {
-                    const double p0 = s_prow[j], p1 = s_prow[j + 32], p2 = s_prow[j + 64], p3 = s_prow[j + 96];
-                    v0 = is_l ? p0 : v0 - f * p0;
-                    v1 = is_l ? p1 : v1 - f * p1;
-                    v2 = is_l ? p2 : v2 - f * p2;
-                    v3 = is_l ? p3 : v3 - f * p3;
-                    dst[j] = v0; dst[j + 32] = v1; dst[j + 64] = v2; dst[j + 96] = v3;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double2 pq = *reinterpret_cast<const double2*>(s_prow + j + 64 * u);
+                        v[u].x = is_l ? pq.x : v[u].x - f * pq.x;
+                        v[u].y = is_l ? pq.y : v[u].y - f * pq.y;
+                        *reinterpret_cast<double2*>(dst + j + 64 * u) = v[u];
+                    }
                 }
                 if (with_dot) {
-                    a0 += v0 * s_ae[j]; a1 += v1 * s_ae[j + 32]; a2 += v2 * s_ae[j + 64]; a3 += v3 * s_ae[j + 96];
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        const double2 e0 = *reinterpret_cast<const double2*>(s_ae + j + 64 * u);
+                        const double2 e1 = *reinterpret_cast<const double2*>(s_ae + j + 64 * (u + 1));
+                        a0 += v[u].x * e0.x; a1 += v[u].y * e0.y;
+                        a2 += v[u + 1].x * e1.x; a3 += v[u + 1].y * e1.y;
+                    }
                 }
             }
-            for (; j < j1; j += 32) {
+            for (; j + 1 < j1; j += 64) {
+                double2 v0 = *reinterpret_cast<const double2*>(src + j);
+                if (wr) {
+                    const double2 pq = *reinterpret_cast<const double2*>(s_prow + j);
+                    v0.x = is_l ? pq.x : v0.x - f * pq.x;
+                    v0.y = is_l ? pq.y : v0.y - f * pq.y;
+                    *reinterpret_cast<double2*>(dst + j) = v0;
+                }
+                if (with_dot) { a0 += v0.x * s_ae[j]; a1 += v0.y * s_ae[j + 1]; }
+            }
+            if (j < j1) {  // odd tail: one last column
                 double v0 = src[j];
                 if (wr) {
                     v0 = is_l ? s_prow[j] : v0 - f * s_prow[j];

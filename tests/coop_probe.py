@@ -88,6 +88,18 @@ print(json.dumps({"case": "C3 depth-1 wave (2 nodes)", "tier": tm["tier"], "grid
                   "kernel_ms": tm["kernel_ms"], "wall_s": time.perf_counter() - t0}), flush=True)
 gm.free_root(root)
 
+# wide waves of HBM-resident LPs: one CTA per LP through the TMA-ring tier 4 vs the cooperative kernel with groups of 1
+for (mm, nn_, cap) in ((1024, 2048, 60), (700, 1200, 60)):
+    base = 4
+    rng2 = np.random.default_rng(42)
+    A4 = np.zeros((base, mm, nn_)); A4[:, :, : nn_ - mm] = rng2.random((base, mm, nn_ - mm)); A4[:, :, nn_ - mm:] = np.eye(mm)
+    b4 = 1.0 + rng2.random((base, mm)); c4 = np.zeros((base, nn_)); c4[:, : nn_ - mm] = -rng2.random((base, nn_ - mm))
+    reps = 148 // base
+    c4, A4, b4 = np.tile(c4, (reps, 1)), np.tile(A4, (reps, 1, 1)), np.tile(b4, (reps, 1))
+    run(f"148 slack-form LPs {mm}x{nn_}, {cap} pivots, tier 4 (TMA ring)", c4, A4, b4, force_tier=4, max_pivots=cap, refactor_period=100000)
+    run(f"148 slack-form LPs {mm}x{nn_}, {cap} pivots, tier 6 G=1", c4, A4, b4, force_tier=6, coop_group=1, max_pivots=cap, refactor_period=100000)
+    run(f"148 slack-form LPs {mm}x{nn_}, {cap} pivots, tier 6 G=2 (74 groups)", c4[:74], A4[:74], b4[:74], force_tier=6, coop_group=2, max_pivots=cap, refactor_period=100000)
+
 # which B&B workloads run through without a solver-failure panic (reference semantics, tree.go:272)
 from gomilp_b200 import status as S  # noqa: E402
 for label, prob, lim in (("c5 n=50", c5_general_integer(50), 4095), ("c5 n=100", c5_general_integer(100), 2047),

@@ -173,6 +173,9 @@ inline V shfl_generic(V v, int src_lane_abs_valid, int src) {
 
 }  // namespace emu
 
+struct alignas(16) double2 {
+    double x, y;
+};
 #define GM_DEV inline
 #define GM_DEV_NOINLINE inline
 inline int gm_tid() { return emu::current()->cur % emu::current()->T; }
