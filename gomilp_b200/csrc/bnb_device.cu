@@ -21,7 +21,9 @@
 // full next wave's descriptors (L x 20 B per node) without a second exchange. Pruning is therefore global and
 // identical to the 1-GPU / 1-worker order. The incumbent's x stays on the rank that solved it and is broadcast once.
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cmath>
@@ -321,6 +323,23 @@ struct Nccl {
 Nccl nccl;
 std::mutex nccl_mu;
 
+// NCCL announces its version on stdout when a process makes its first communicator; callers of this library own
+// stdout (bench.py prints exactly one JSON line), so the announcement goes to /dev/null.
+struct StdoutSilencer {
+    int saved = -1;
+    StdoutSilencer() {
+        fflush(stdout);
+        saved = dup(1);
+        const int devnull = open("/dev/null", O_WRONLY);
+        if (saved >= 0 && devnull >= 0) dup2(devnull, 1);
+        if (devnull >= 0) close(devnull);
+    }
+    ~StdoutSilencer() {
+        fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+    }
+};
+
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, device = -1;
@@ -366,7 +385,10 @@ int gm_comm_unique_id(void* id128) {
     std::lock_guard<std::mutex> lk(nccl_mu);
     if (!nccl.load()) { t_err = "libnccl.so.2 not found"; return GM_ERR_CUDA; }
     ncclUniqueId id;
-    NK(nccl.GetUniqueId(&id));
+    {
+        StdoutSilencer quiet;
+        NK(nccl.GetUniqueId(&id));
+    }
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     std::memcpy(id128, &id, 128);
     return GM_OK;
@@ -385,7 +407,10 @@ int gm_comm_init(int32_t rank, int32_t world, const void* id128) {
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
     ncclComm_t c = nullptr;
-    NK(nccl.CommInitRank(&c, world, id, rank));
+    {
+        StdoutSilencer quiet;
+        NK(nccl.CommInitRank(&c, world, id, rank));
+    }
     t_comm.comm = c;
     t_comm.rank = rank;
     t_comm.world = world;

@@ -151,17 +151,18 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
     // tier 6 (cooperative): fewer LPs than SMs and an LP big enough that one CTA per LP would crawl
     int G = 0;
     if (d.coop_ok && m < n) {
-        G = opt.coop_group > 0 ? opt.coop_group : d.sms / P.count;
+        G = opt.coop_group > 0 ? opt.coop_group : std::max(1, d.sms / P.count);
         G = std::min(G, std::max(1, m / 2));
-        G = std::min(G, d.sms);
-        if ((long long)G * P.count > d.sms) G = d.sms / P.count;
+        G = std::max(1, std::min(G, d.sms));
     }
     const gm::CoopLayout cl = gm::coop_layout(m, n, kHbmThreads, G > 0 ? G : 1, d.smem_optin - 512);
     const bool fits_coop = G >= 1 && cl.smem_bytes + 256 <= d.smem_optin;
     int tier = opt.force_tier;
     if (tier == 0) {
         tier = fits_reg ? 1 : (fits_smem ? 2 : (fits_bismem ? 3 : (fits_small ? 4 : 5)));
-        if (tier >= 2 && fits_coop && G >= 2 && m >= 96) tier = 6;
+        // more SMs than LPs: several CTAs per LP. HBM-resident shapes: always (with one CTA per LP its fused
+        // update + FTRAN pass still moves 2 m^2 instead of 3 m^2 words per pivot and beats the TMA-ring tier 4).
+        if (fits_coop && ((tier >= 2 && G >= 2 && m >= 96) || tier >= 4)) tier = 6;
     }
     if ((tier == 1 && !fits_reg) || (tier == 2 && !fits_smem) || (tier == 3 && !fits_bismem) ||
         (tier == 4 && !fits_small) || (tier == 6 && !fits_coop) || tier < 1 || tier > 6)

@@ -1742,6 +1742,17 @@ struct SolverT {
                 const double* wc = W + m + (valid ? k : 0);
                 double a0 = 0, a1 = 0;
                 int i = q;
+                // tier 3 reads W from HBM / L2: eight independent loads per trip, or the walk is one L2 latency per row
+                for (; i + 28 < m; i += 32) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = wc[(size_t)(i + 4 * u) * ldw];
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        a0 += y[i + 4 * u] * v[u];
+                        a1 += y[i + 4 * u + 4] * v[u + 1];
+                    }
+                }
                 for (; i + 4 < m; i += 8) {
                     a0 += y[i] * wc[(size_t)i * ldw];
                     a1 += y[i + 4] * wc[(size_t)(i + 4) * ldw];

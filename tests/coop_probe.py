@@ -100,9 +100,16 @@ for (mm, nn_, cap) in ((1024, 2048, 60), (700, 1200, 60)):
     run(f"148 slack-form LPs {mm}x{nn_}, {cap} pivots, tier 6 G=1", c4, A4, b4, force_tier=6, coop_group=1, max_pivots=cap, refactor_period=100000)
     run(f"148 slack-form LPs {mm}x{nn_}, {cap} pivots, tier 6 G=2 (74 groups)", c4[:74], A4[:74], b4[:74], force_tier=6, coop_group=2, max_pivots=cap, refactor_period=100000)
 
+# wide batches of mid-size LPs: the one-CTA-per-LP tiers 2 / 3 vs the cooperative kernel with groups of 1
+for (mm, nn_, cnt, tier_) in ((150, 300, 296, 3), (100, 200, 296, 3), (70, 140, 592, 2), (150, 250, 2048, 3)):
+    cB, AB, bB = feasible_bounded_lp(np.random.default_rng(5), mm, nn_, cnt)
+    run(f"{cnt} LPs {mm}x{nn_} tier {tier_}", cB, AB, bB, force_tier=tier_)
+    run(f"{cnt} LPs {mm}x{nn_} tier 6 G=1", cB, AB, bB, force_tier=6, coop_group=1)
+
 # which B&B workloads run through without a solver-failure panic (reference semantics, tree.go:272)
 from gomilp_b200 import status as S  # noqa: E402
 for label, prob, lim in (("c5 n=50", c5_general_integer(50), 4095), ("c5 n=100", c5_general_integer(100), 2047),
+                         ("c5 n=100 deep", c5_general_integer(100), 16383),
                          ("c5 n=200", c5_general_integer(200), 511), ("knapsack 60x10", knapsack(np.random.default_rng(7), 60, 10), 4095),
                          ("knapsack 120x40", knapsack(np.random.default_rng(7), 120, 40), 1023),
                          ("knapsack 500x200 (C3)", knapsack(np.random.default_rng(7), 500, 200), 63)):

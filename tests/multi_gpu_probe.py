@@ -80,15 +80,41 @@ def main():
     args = ap.parse_args()
     one = run(1, args)[0]
     many = run(args.world, args) if args.world > 1 else [one]
-    ok = True
+    # The search must be the same search: status, node and wave counts and every decision identical. The LP arithmetic
+    # is NOT bit-identical across GPU counts (a rank's block is a smaller launch, which can select another tier or
+    # another number of CTAs per LP, i.e. another summation order), so z and x are compared at the 1e-9 parity bar.
+    def close(a, b):
+        if a is None or b is None:
+            return a is None and b is None
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        return a.shape == b.shape and bool(np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(b))))
+
+    def same_log(la, lb):
+        if len(la) != len(lb):
+            return False
+        for ra, rb in zip(la, lb):
+            if tuple(ra[:4]) != tuple(rb[:4]) or tuple(ra[5:7]) != tuple(rb[5:7]):
+                return False
+            if not (ra[4] != ra[4] and rb[4] != rb[4]) and not close(ra[4], rb[4]):
+                return False
+        return True
+
+    ok, diffs = True, []
     for o in many:
-        same = (o["status"], o["lp_status"], o["nodes"], o["waves"], o["pivots"], o["z"], o["x"]) == \
-               (one["status"], one["lp_status"], one["nodes"], one["waves"], one["pivots"], one["z"], one["x"])
-        same = same and (not args.log or o["log"] == one["log"])
-        ok = ok and same
+        for key in ("status", "lp_status", "nodes", "waves"):
+            if o[key] != one[key]:
+                ok = False
+                diffs.append(f"rank {o['rank']}: {key} {o[key]} vs {one[key]}")
+        if not close(o["z"], one["z"]) or not close(o["x"], one["x"]):
+            ok = False
+            diffs.append(f"rank {o['rank']}: z / x beyond 1e-9")
+        if args.log and not same_log(o["log"], one["log"]):
+            ok = False
+            diffs.append(f"rank {o['rank']}: decision log")
     wall = max(o["wall_s"] for o in many)
     print(json.dumps({"workload": f"{args.kind} n={args.n} m={args.m} seed={args.seed} FIXED most-infeasible, node budget "
-                      f"{args.nodes}, device-side scan", "world": args.world, "identical_to_1gpu": ok,
+                      f"{args.nodes}, device-side scan", "world": args.world, "identical_to_1gpu": ok, "differences": diffs,
+                      "pivots_multi": many[0]["pivots"],
                       "status": one["status"], "lp_status": one["lp_status"], "nodes": one["nodes"], "waves": one["waves"],
                       "pivots": one["pivots"], "nodes_per_sec_1gpu": one["nodes"] / one["wall_s"],
                       "nodes_per_sec": one["nodes"] / wall, "wall_s_1gpu": one["wall_s"], "wall_s": wall,
