@@ -209,7 +209,7 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
             gm.capi.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
         from problems import c5_general_integer
         p = c5_general_integer(100)   # C5, n = 100: 150 x 250 + depth, wide waves of 2048 node LPs
-        limit = 4095
+        limit = 16383
         best = None
         for rep in range(3):
             if dist is not None:
@@ -227,7 +227,7 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
         if world > 1:
             gm.capi.comm_destroy()
         return {"workload": "C5 general-integer MILP n=100 (150x250 + depth, bounds as rows), FIXED most-infeasible, node "
-                            "budget 4095, device-side scan, FIFO blocks per rank, cold children, best of 2 after a warm-up run",
+                            "budget 16383, device-side scan, FIFO blocks per rank, cold children, best of 2 after a warm-up run",
                 "gpus": world, "nodes": r.nodes, "waves": r.waves, "pivots": r.pivots, "status": r.status,
                 "wall_s_max_over_ranks": float(t[0]), "nodes_per_sec": r.nodes / float(t[0]), "device_ms": r.device_ms,
                 "collective": "ncclAllGather of 32-byte node records, once per wave" if world > 1 else "none"}
