@@ -39,6 +39,9 @@ GM_DEV void gm_threadfence() { __threadfence(); }
 GM_DEV void gm_spin_pause() {}
 GM_DEV long long gm_clock() { return clock64(); }
 GM_DEV void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+GM_DEV void gm_red_release_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 GM_DEV unsigned long long gm_ld_acquire_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -201,12 +201,12 @@ inline CoopLayout coop_layout(int m, int n, int T, int G, size_t smem_limit = 20
     // The inversion panel (m x 17 doubles, 16 columns + 1 of padding) plus a column and a row vector ALIAS the
     // main-loop scratch above: an inversion only runs between main-loop calls, when all of it is dead.
     const size_t pan = (size_t)m * 17 + mp + 32;
-    const size_t tail = (size_t)T + (mp + 1) / 2 + ((size_t)T + 1) / 2;
+    const size_t tail = 2 * (size_t)T + (mp + 1) / 2 + (2 * (size_t)T + 1) / 2;
     c.pan_nb = ((pan > q ? pan : q) + tail) * sizeof(double) + 1024 <= smem_limit ? 16 : 0;
     if (c.pan_nb && pan > q) q = pan;
-    c.s_red = q; q += (size_t)T;
+    c.s_red = q; q += 2 * (size_t)T;    // two halves, used alternately by the block reductions
     c.s_bit = q; q += (mp + 1) / 2;     // ints
-    c.s_redi = q; q += ((size_t)T + 1) / 2;  // ints
+    c.s_redi = q; q += (2 * (size_t)T + 1) / 2;  // ints
     c.smem_bytes = q * sizeof(double);
     return c;
 }
@@ -285,6 +285,16 @@ struct SolverT {
     GM_DEV double src_b(int i) const { return i < m0 ? gm_ldg(b0 + i) : brhs[i - m0]; }
 
     // ---- block-wide reductions (result identical in every thread) ---------------------------------
+    // COOP: the scratch has two halves used alternately, so a reduction needs one barrier instead of two (the next
+    // reduction writes the other half; by the barrier after that every thread has finished reading this one).
+    int red_flip;
+    GM_DEV int red_base() {
+        if constexpr (COOP) { red_flip ^= 1; return red_flip ? gm_nthreads() : 0; }
+        return 0;
+    }
+    GM_DEV void red_tail_sync() {
+        if constexpr (!COOP) gm_sync();
+    }
     // first minimum over f(k), NaN skipped, all-NaN -> index 0: floats.MinIdx, floats.go:458-474
     template <class F>
     GM_DEV MinLoc block_argmin(int len, F f) {
@@ -301,16 +311,17 @@ struct SolverT {
             if (oi != INT_MAX && (bi == INT_MAX || ov < bvv || (ov == bvv && oi < bi))) { bvv = ov; bi = oi; }
         }
         const int nw = T >> 5;
-        if ((t & 31) == 0) { red[t >> 5] = bvv; redi[t >> 5] = bi; }
+        const int rb = red_base();
+        if ((t & 31) == 0) { red[rb + (t >> 5)] = bvv; redi[rb + (t >> 5)] = bi; }
         gm_sync();
-        bvv = red[0];
-        bi = redi[0];
+        bvv = red[rb];
+        bi = redi[rb];
         for (int w = 1; w < nw; ++w) {
-            const double ov = red[w];
-            const int oi = redi[w];
+            const double ov = red[rb + w];
+            const int oi = redi[rb + w];
             if (oi != INT_MAX && (bi == INT_MAX || ov < bvv || (ov == bvv && oi < bi))) { bvv = ov; bi = oi; }
         }
-        gm_sync();
+        red_tail_sync();
         MinLoc out;
         out.v = bvv;
         out.i = bi == INT_MAX ? 0 : bi;
@@ -325,11 +336,12 @@ struct SolverT {
         for (int k = t; k < len; k += T) s += f(k);
         for (int d = 16; d >= 1; d >>= 1) s += gm_shfl_xor(s, d);
         const int nw = T >> 5;
-        if ((t & 31) == 0) red[t >> 5] = s;
+        const int rb = red_base();
+        if ((t & 31) == 0) red[rb + (t >> 5)] = s;
         gm_sync();
         s = 0;
-        for (int w = 0; w < nw; ++w) s += red[w];
-        gm_sync();
+        for (int w = 0; w < nw; ++w) s += red[rb + w];
+        red_tail_sync();
         return s;
     }
 
@@ -343,11 +355,12 @@ struct SolverT {
         }
         for (int d = 16; d >= 1; d >>= 1) s = fmax(s, gm_shfl_xor(s, d));
         const int nw = T >> 5;
-        if ((t & 31) == 0) red[t >> 5] = s;
+        const int rb = red_base();
+        if ((t & 31) == 0) red[rb + (t >> 5)] = s;
         gm_sync();
         s = 0;
-        for (int w = 0; w < nw; ++w) s = fmax(s, red[w]);
-        gm_sync();
+        for (int w = 0; w < nw; ++w) s = fmax(s, red[rb + w]);
+        red_tail_sync();
         return s;
     }
 
@@ -364,11 +377,12 @@ struct SolverT {
             s = o < s ? o : s;
         }
         const int nw = T >> 5;
-        if ((t & 31) == 0) redi[t >> 5] = s;
+        const int rb = red_base();
+        if ((t & 31) == 0) redi[rb + (t >> 5)] = s;
         gm_sync();
         s = INT_MAX;
-        for (int w = 0; w < nw; ++w) s = redi[w] < s ? redi[w] : s;
-        gm_sync();
+        for (int w = 0; w < nw; ++w) s = redi[rb + w] < s ? redi[rb + w] : s;
+        red_tail_sync();
         return s;
     }
 
@@ -425,6 +439,7 @@ struct SolverT {
             if (G == 1) {
                 if (j < no) out[j] = (base ? base[j] : 0.0) + sgn * acc;
             } else {  // no <= S here: a single pass over j
+                if constexpr (COOP) gm_sync();  // a barrier-less block reduction may still be reading this scratch
                 red[t] = acc;
                 gm_sync();
                 if (t < no) {
@@ -1912,11 +1927,11 @@ struct SolverT {
         if (G > 1) {
             ++epoch;
             if (gm_tid() == 0) {
-                gm_threadfence();
-                gm_atomic_add_u64(gbar, 1ull);
+                // release: the CTA's writes so far (ordered before this by the block barrier) become visible before the
+                // arrival is; acquire: nothing after the spin is satisfied from before the last arrival
+                gm_red_release_add_u64(gbar, 1ull);
                 const unsigned long long target = epoch * (unsigned long long)G;
                 while (gm_ld_acquire_u64(gbar) < target) gm_spin_pause();
-                gm_threadfence();
             }
             gm_sync();
         }
@@ -2764,7 +2779,7 @@ struct SolverT {
     // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
     GM_DEV void bind_workspace(const BatchParams& P, double* wbase, double* bibase, double* small,
                                double* ring_base = nullptr, unsigned long long* bars = nullptr) {
-        G = 1; rank = 0; gbar = nullptr; epoch = 0; mail = nullptr;
+        G = 1; rank = 0; gbar = nullptr; epoch = 0; mail = nullptr; red_flip = 0;
         ring = ring_base; ring_bar = bars; ring_ns = P.ring_stages; ring_stage_doubles = P.ring_stage_bytes / 8;
         ring_uses = 0;
         stream_min_m = P.stream_min_m;

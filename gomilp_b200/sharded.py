@@ -23,6 +23,8 @@ import math
 import time
 from dataclasses import dataclass, field
 
+import hashlib
+
 import numpy as np
 
 from . import status as S
@@ -279,8 +281,12 @@ def gpu_wave_solver():
     cache = {}
 
     def solve(c0, A0, b0, bvar, bsign, brhs):
-        key = id(A0)
+        # keyed on the contents, not on id(): an id can be reused by another array after the first one is collected
+        key = (A0.shape, hashlib.sha256(np.ascontiguousarray(A0).tobytes()).digest(),
+               hashlib.sha256(np.ascontiguousarray(b0).tobytes() + np.ascontiguousarray(c0).tobytes()).digest())
         if key not in cache:
+            for h in cache.values():      # a new root replaces the cached one: release it on the device first
+                capi.free_root(h)
             cache.clear()
             cache[key] = capi.upload_root(c0, A0, b0)
         m0, n0 = A0.shape

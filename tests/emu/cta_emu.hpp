@@ -283,6 +283,7 @@ inline void gm_threadfence() {}
 inline void gm_spin_pause() { emu::yield_as(emu::RUN); }
 inline long long gm_clock() { return 0; }
 inline void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+inline void gm_red_release_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 inline unsigned long long gm_ld_acquire_u64(const unsigned long long* p) { return *(volatile const unsigned long long*)p; }
 // D(8x8) = A(8x4) * B(4x8) + C with the m8n8k4 fragment layout of mma.sync (see cta_rt.cuh)
 inline void gm_dmma_8x8x4(double& c0, double& c1, double a, double b) {

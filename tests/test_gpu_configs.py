@@ -319,3 +319,48 @@ def test_two_host_threads_on_one_device_do_not_interfere():
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+@pytest.mark.timeout(600)
+def test_warm_started_waves_match_the_oracle_children():
+    """gm_solve_wave_warm against the ORACLE (the warm-start test compared the GPU with itself): the C5
+    fixtures' children, each started from its parent's final basis / inverse kept in HBM, must reach the oracle's cold
+    optimum (status, z, x at 1e-9) in fewer pivots."""
+    for n in (50, 100):
+        z = np.load(os.path.join(GOLD, f"c5_general_n{n}.npz"))
+        p = c5_general_integer(n)
+        c0, A0, b0 = standard_form(p)
+        m0, n0 = A0.shape
+        root = gm.upload_root(c0, A0, b0)
+        cold_piv = warm_piv = 0
+        try:
+            prev_idx = None
+            for L in sorted(set(int(v) for v in z["L"])):
+                idx = np.nonzero(z["L"] == L)[0]
+                bvar = z["bvar"][idx, :L].astype(np.int32).reshape(len(idx), L)
+                bsign = z["bsign"][idx, :L].reshape(len(idx), L)
+                brhs = z["brhs"][idx, :L].reshape(len(idx), L)
+                parent = np.full(len(idx), -1, dtype=np.int32)
+                if prev_idx is not None:  # the parent is the node of the previous wave whose rows are my prefix
+                    for q, k in enumerate(idx):
+                        for pq, pk in enumerate(prev_idx):
+                            if (np.array_equal(z["bvar"][pk, :L - 1], z["bvar"][k, :L - 1]) and
+                                    np.array_equal(z["bsign"][pk, :L - 1], z["bsign"][k, :L - 1]) and
+                                    np.array_equal(z["brhs"][pk, :L - 1], z["brhs"][k, :L - 1])):
+                                parent[q] = pq
+                                break
+                    assert (parent >= 0).all()
+                w = gm.solve_wave(root, n0, m0, bvar, bsign, brhs, parent=parent, warm=True)
+                for q, k in enumerate(idx):
+                    assert w.status[q] == int(z["status"][k])
+                    if int(z["status"][k]) == S.GM_OK:
+                        assert rel(w.z[q], z["z"][k]) <= RTOL and rel(w.x[q], z["x"][k]) <= RTOL
+                    if L > 0:
+                        warm_piv += int(w.stats[q, 0] + w.stats[q, 1])
+                        cold_piv += int(z["piv1"][k] + z["piv2"][k])
+                prev_idx = idx
+        finally:
+            gm.free_root(root)
+        report(f"warm-started children, C5 n={n}: oracle optimum reproduced at 1e-9 on every node; {warm_piv} pivots "
+               f"against {cold_piv} for the oracle's cold solves ({cold_piv / max(1, warm_piv):.1f}x fewer)")
+        assert warm_piv < cold_piv
