@@ -190,6 +190,16 @@ def bnb_extra(gm):
         p5 = c5_general_integer(200)
         out["c5_n200"] = {"workload": "C5: general-integer MILP n=200 (300x500 + depth), FIXED most-infeasible, node budget "
                                       "511, device-side scan, cold children", **row(*best_of(p5, 1 | 8, 511, reps=2))}
+        p51 = c5_general_integer(100)
+        gm.milp_solve(p51["c"], None, None, p51["G"], p51["h"], p51["integrality"], mode=1 | 4 | 8, heuristic=1,
+                      node_limit=512, keep_log=False)
+        out["c5_n100"] = {"workload": "C5: general-integer MILP n=100 (150x250 + depth), FIXED most-infeasible, node budget "
+                                      "16383, device-side scan, best of 2",
+                          "cold_children": row(*best_of(p51, 1 | 8, 16383, reps=2)),
+                          "warm_started_children": row(*best_of(p51, 1 | 4 | 8, 16383, reps=2)),
+                          "note": "warm start (the north star's 'children warm-start from the parent basis'): every node's "
+                                  "final basis and inverse stay in HBM, a child starts from [B 0; g 1]^-1; same optima, not "
+                                  "a pivot-for-pivot replay of the reference's cold solves"}
     except Exception as e:  # never let the extra break the contract line
         out["error"] = repr(e)
     return out
@@ -351,6 +361,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def p(a):
         return a.ctypes.data_as(C.c_void_p)
 
+    if args.no_streamed:
+        gm.set_options(no_streamed_batch=True)
+
     def e2e_step():
         rc = L.gm_simplex_batch(BATCH, p(cn), p(An), p(bn), M, N, 0.0, p(hs), p(hF), p(hx), p(hB), p(hS))
         assert rc == 0, rc
@@ -363,6 +376,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     e2e_tm = gm.last_timing()
+    gm.set_options()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(hs, status) and np.allclose(hF, d_optF.cpu().numpy(), rtol=0, atol=0)
@@ -377,7 +391,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         pivots_all = pivots
     total_ms, e2e_ms = float(t[0]), float(t[1])
     # extras, outside the timed region. The sharded B&B is collective: every rank takes part.
-    bnb_sh = bnb_sharded_extra(gm, dist, dev, rank, world)
+    bnb_sh = bnb_sharded_extra(gm, dist, dev, rank, world) if not args.quick else {"skipped": "--quick"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -408,7 +422,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "breakdown_last_step_ms": {"h2d": e2e_tm["h2d_ms"], "kernel": e2e_tm["kernel_ms"], "d2h": e2e_tm["d2h_ms"]},
-                "api": "gm_simplex_batch (C ABI, pinned host buffers)"},
+                "api": "gm_simplex_batch (C ABI, pinned host buffers)",
+                "launches_last_step": e2e_tm["launches"],
+                "path": "one launch per slice" if args.no_streamed else "one launch, CTAs gated on the copy stream's "
+                        "arrival counter (the batch crosses PCIe while the first LPs are being solved)"},
         "gpu_launches": args.steps,
         # Tier 1 keeps B^-1 in registers and W in shared memory: the per-pivot bytes never reach HBM (the batch is
         # read from HBM once per launch), so the roof that bounds this kernel is the SM's shared-memory / issue
@@ -448,6 +465,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the B&B / HBM-tier extras (profiling runs)")
+    ap.add_argument("--no-streamed", action="store_true",
+                    help="e2e through one launch per slice instead of one launch gated on arrival counters: required "
+                         "under ncu, whose kernel replay serialises launches (a kernel that waits for a copy issued "
+                         "after it would never see it)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -457,7 +478,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
-               str(args.warmup), "--impl", args.impl] + (["--quick"] if args.quick else [])
+               str(args.warmup), "--impl", args.impl] + (["--quick"] if args.quick else []) + \
+              (["--no-streamed"] if args.no_streamed else [])
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -115,8 +115,9 @@ def init(device: int = 0):
 
 
 def set_options(max_pivots: int = 0, refactor_period: int = 0, force_tier: int = 0, no_tma_ring: bool = False,
-                coop_group: int = 0):
-    o = gm_options(max_pivots, refactor_period, force_tier, 1 if no_tma_ring else 0, coop_group, 0)
+                coop_group: int = 0, no_streamed_batch: bool = False):
+    o = gm_options(max_pivots, refactor_period, force_tier, 1 if no_tma_ring else 0, coop_group,
+                   1 if no_streamed_batch else 0)
     _check(lib().gm_set_options(C.byref(o)))
 
 

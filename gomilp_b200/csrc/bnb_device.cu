@@ -132,6 +132,14 @@ __global__ void __launch_bounds__(128) node_check(int nodes, int n0, const int* 
     }
 }
 
+// Warm-started waves: the nodes whose warm start died (GM_ERR_WARM_RETRY) are re-solved cold by a second launch over
+// this list. out[0] = how many.
+__global__ void __launch_bounds__(256) warm_retry_list(int nodes, const int* __restrict__ status, int* __restrict__ list,
+                                                       int* __restrict__ out) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nodes; k += gridDim.x * blockDim.x)
+        if (status[k] == GM_ERR_WARM_RETRY) list[atomicAdd(out, 1)] = k;
+}
+
 // checkSolution over the whole wave in FIFO order, one CTA. See the file header for why it is a scan.
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads) wave_scan(int count, int wave_no, int L, const NodeRec* __restrict__ rec,
@@ -478,6 +486,10 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
         Buf desc_v[2] = {Buf(st), Buf(st)}, desc_s[2] = {Buf(st), Buf(st)}, desc_r[2] = {Buf(st), Buf(st)};
         Buf par[2] = {Buf(st), Buf(st)}, ids[2] = {Buf(st), Buf(st)};
         Buf d_status(st), d_z(st), d_x(st), d_stats(st);
+        // warm start (GM_BNB_WARM_START, one GPU): every node's final basis and inverse stay in HBM for its children
+        Buf wbi[2] = {Buf(st), Buf(st)}, wbasis[2] = {Buf(st), Buf(st)}, d_retry(st), d_nretry(st);
+        int* h_nretry = nullptr;
+        bool prev_kept = false;
         WaveSummary* h_sum = nullptr;
         std::vector<NodeRec> h_rec;
         std::vector<int> h_dec, h_par;
@@ -502,6 +514,8 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
         std::vector<long long> prev_ids;  // ids of the previous wave (parents), kept only for the decision callback
 
         CKE(cudaMallocHost(&h_sum, sizeof(WaveSummary)));
+        CKE(cudaMallocHost(&h_nretry, sizeof(int)));
+        CKE(d_nretry.reserve(sizeof(int)));
         CKE(d_integ.reserve(n0));
         CKE(cudaMemcpyAsync(d_integ.p, integ.data(), n0, cudaMemcpyHostToDevice, st));
         CKE(d_sum.reserve(sizeof(WaveSummary)));
@@ -551,9 +565,47 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
                 }
                 P.status = d_status.as<int>(); P.optF = d_z.as<double>(); P.x = d_x.as<double>();
                 P.stats = d_stats.as<int>();
+                const int m = (int)m0 + L;
+                bool keep = false, warmed = false;
+                if (warm && world == 1) {  // children continue from [B 0; g 1]^-1 read off the parent's inverse
+                    size_t free_b = 0, total_b = 0;
+                    cudaMemGetInfo(&free_b, &total_b);
+                    keep = ((size_t)mine * m * m * 8 + (size_t)mine * m * 8) * 2 < free_b / 2;
+                    if (keep) {
+                        CKE(wbi[cur].reserve((size_t)mine * m * m * 8));
+                        CKE(wbasis[cur].reserve((size_t)mine * m * 8));
+                        CKE(cudaMemsetAsync(wbasis[cur].p, 0xff, (size_t)mine * m * 8, st));  // "no basis" unless written
+                        P.bi_out = wbi[cur].as<double>();
+                        P.basis = wbasis[cur].as<long long>();
+                    }
+                    if (wave_no > 0 && prev_kept) {
+                        P.warm_parent = par[cur].as<int>();   // written by the previous wave's scan
+                        P.warm_basis = wbasis[cur ^ 1].as<long long>();
+                        P.warm_bi = wbi[cur ^ 1].as<double>();
+                        warmed = true;
+                    }
+                }
                 gm_timing tm{};
                 engine_rc = launch_wave(*d, P, st, nullptr, nullptr, &tm);
                 if (engine_rc != GM_OK) goto done;
+                if (warmed) {  // a warm path that died is re-solved from scratch, in place
+                    CKE(d_retry.reserve(sizeof(int) * mine));
+                    CKE(cudaMemsetAsync(d_nretry.p, 0, sizeof(int), st));
+                    warm_retry_list<<<(unsigned)std::min<int64_t>(64, (mine + 255) / 256), 256, 0, st>>>(
+                        (int)mine, d_status.as<int>(), d_retry.as<int>(), d_nretry.as<int>());
+                    CKE(cudaGetLastError());
+                    CKE(cudaMemcpyAsync(h_nretry, d_nretry.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    CKE(cudaStreamSynchronize(st));
+                    if (*h_nretry > 0) {
+                        gm::BatchParams Q = P;
+                        Q.warm_parent = nullptr;
+                        Q.lp_list = d_retry.as<int>();
+                        Q.count = *h_nretry;
+                        engine_rc = launch_wave(*d, Q, st, nullptr, nullptr, &tm);
+                        if (engine_rc != GM_OK) goto done;
+                    }
+                }
+                prev_kept = keep;
                 node_check<<<(unsigned)mine, 128, 0, st>>>((int)mine, (int)n0, d_status.as<int>(), d_z.as<double>(),
                                                             d_x.as<double>(), d_stats.as<int>(),
                                                             d_integ.as<unsigned char>(), r.c, bmode, heuristic,
@@ -641,6 +693,7 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
     done:
         cudaStreamSynchronize(st);
         if (h_sum) cudaFreeHost(h_sum);
+        if (h_nretry) cudaFreeHost(h_nretry);
 #undef CKE
 #undef NKE
     }

@@ -38,6 +38,17 @@ GM_DEV int gm_block_id() { return (int)blockIdx.x; }
 GM_DEV void gm_threadfence() { __threadfence(); }
 GM_DEV void gm_spin_pause() {}
 GM_DEV long long gm_clock() { return clock64(); }
+// Waits until *ready > item (a counter the copy engine advances from another stream, hence system scope). Bounded:
+// ~10 s of polling, then false.
+GM_DEV bool gm_wait_ready(const int* ready, int item) {
+    for (int spin = 0; spin < (1 << 25); ++spin) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+        if (v > item) return true;
+        __nanosleep(256);
+    }
+    return false;
+}
 GM_DEV void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 GM_DEV void gm_red_release_add_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

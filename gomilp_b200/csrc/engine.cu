@@ -29,9 +29,11 @@ int fail(cudaError_t e, const char* what) {
 cudaError_t StreamEvents::init() {
     cudaError_t r = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && r == cudaSuccess; ++i) r = cudaEventCreate(&e[i]);
+    if (r == cudaSuccess) r = cudaMallocHost(&h_counts, 64 * sizeof(int));
     return r;
 }
 StreamEvents::~StreamEvents() {
+    if (h_counts) cudaFreeHost(h_counts);
     for (auto& ev : e)
         if (ev) cudaEventDestroy(ev);
     if (s) cudaStreamDestroy(s);
@@ -576,6 +578,74 @@ static int run_host_batch_pipelined(DeviceCtx& d, gm::BatchParams P, const doubl
     return rc;
 }
 
+// Large PINNED host batches: ONE launch. The kernel starts at once and its CTAs pull LPs from the queue, but an LP is
+// only started when the copy stream's arrival counter says its inputs are in HBM (BatchParams::ready); the batch crosses
+// PCIe in slices on a second stream while the kernel is already solving the first ones. Compared with one launch per
+// slice (run_host_batch_pipelined) there is no under-filled tail per slice: the time is max(copy, solve) plus the
+// results' trip back.
+static int run_host_batch_streamed(DeviceCtx& d, gm::BatchParams P, const double* h_c, const double* h_A,
+                                   const double* h_b, int32_t* status, double* optF, double* optX, int64_t* basis,
+                                   int32_t* stats) {
+    const int64_t count = P.count, m = P.m0, n = P.n0;
+    StreamLease lk(&d), lc(&d);
+    CK(lk.err); CK(lc.err);
+    cudaStream_t ks = lk.se->s, cs = lc.se->s;
+    DevBuf dc(ks), dA(ks), db(ks), dF(ks), dX(ks), dst(ks), dB(ks), dS(ks), dready(ks);
+    CK(dc.alloc(sizeof(double) * count * n));
+    CK(dA.alloc(sizeof(double) * count * m * n));
+    CK(db.alloc(sizeof(double) * count * m));
+    CK(dF.alloc(sizeof(double) * count));
+    CK(dX.alloc(sizeof(double) * count * n));
+    CK(dst.alloc(sizeof(int32_t) * count));
+    if (basis) CK(dB.alloc(sizeof(long long) * count * m));
+    if (stats) CK(dS.alloc(sizeof(int32_t) * count * 8));
+    CK(dready.alloc(sizeof(int)));
+    CK(cudaMemsetAsync(dready.p, 0, sizeof(int), ks));
+    CK(cudaEventRecord(lk.se->e[0], ks));         // buffers exist, counter is zero
+    CK(cudaStreamWaitEvent(cs, lk.se->e[0], 0));
+    P.c = dc.as<double>(); P.A = dA.as<double>(); P.b = db.as<double>(); P.lda = (int)n;
+    P.status = dst.as<int>(); P.optF = dF.as<double>(); P.x = dX.as<double>(); P.x_stride = n;
+    P.basis = basis ? dB.as<long long>() : nullptr;
+    P.stats = stats ? dS.as<int>() : nullptr;
+    P.ready = dready.as<int>();
+    t_timing = gm_timing{};
+    int rc = launch_wave(d, P, ks, lk.se->e[1], lk.se->e[2], &t_timing);   // spins on `ready` until data arrives
+    // slices of the batch, then the new arrival count, on the copy stream (pinned memory: truly asynchronous)
+    const int slices = (int)std::min<int64_t>(48, std::max<int64_t>(1, count / 128));
+    const int64_t per = (count + slices - 1) / slices;
+    int* hc = lc.se->h_counts;
+    CK(cudaEventRecord(lc.se->e[0], cs));
+    for (int k = 0; k < slices && rc == GM_OK; ++k) {
+        const int64_t off = k * per, cnt = std::min<int64_t>(per, count - off);
+        if (cnt <= 0) break;
+        CK(cudaMemcpyAsync(dc.as<double>() + off * n, h_c + off * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(db.as<double>() + off * m, h_b + off * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(dA.as<double>() + off * m * n, h_A + off * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
+        hc[k] = (int)(off + cnt);
+        CK(cudaMemcpyAsync(dready.p, &hc[k], sizeof(int), cudaMemcpyHostToDevice, cs));
+    }
+    if (rc != GM_OK) {  // the launch failed: make sure nothing is left waiting, then report
+        hc[63] = (int)count;
+        cudaMemcpyAsync(dready.p, &hc[63], sizeof(int), cudaMemcpyHostToDevice, cs);
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(ks);
+        return rc;
+    }
+    CK(cudaEventRecord(lc.se->e[1], cs));
+    CK(cudaMemcpyAsync(status, dst.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ks));
+    CK(cudaMemcpyAsync(optF, dF.p, sizeof(double) * count, cudaMemcpyDeviceToHost, ks));
+    CK(cudaMemcpyAsync(optX, dX.p, sizeof(double) * count * n, cudaMemcpyDeviceToHost, ks));
+    if (basis) CK(cudaMemcpyAsync(basis, dB.p, sizeof(int64_t) * count * m, cudaMemcpyDeviceToHost, ks));
+    if (stats) CK(cudaMemcpyAsync(stats, dS.p, sizeof(int32_t) * count * 8, cudaMemcpyDeviceToHost, ks));
+    CK(cudaEventRecord(lk.se->e[3], ks));
+    CK(cudaStreamSynchronize(cs));
+    CK(cudaStreamSynchronize(ks));
+    t_timing.h2d_ms = ms(lc.se->e[0], lc.se->e[1]);
+    t_timing.kernel_ms = ms(lk.se->e[1], lk.se->e[2]);  // includes waiting for arrivals
+    t_timing.d2h_ms = ms(lk.se->e[2], lk.se->e[3]);
+    return GM_OK;
+}
+
 extern "C" {
 
 int gm_simplex_batch(int64_t count, const double* c, const double* A, const double* b, int64_t m, int64_t n,
@@ -594,7 +664,17 @@ int gm_simplex_batch(int64_t count, const double* c, const double* A, const doub
     const double in_bytes = (double)count * (double)(m * n + m + n) * 8.0;
     int chunks = (int)std::min<int64_t>(8, count / (4 * (int64_t)d->sms));
     if (in_bytes < 32e6 || t_trace.armed) chunks = 1;
-    if (chunks >= 2) return run_host_batch_pipelined(*d, P, c, A, b, status, optF, optX, basis, stats, chunks);
+    if (chunks >= 2) {
+        // pinned inputs (cudaHostAlloc / cudaHostRegister / torch pin_memory): one launch gated on arrival counters
+        cudaPointerAttributes pa, pb, pc;
+        const bool pinned = g.opt.reserved2 != 1 &&
+                            cudaPointerGetAttributes(&pa, A) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&pb, b) == cudaSuccess && pb.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&pc, c) == cudaSuccess && pc.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) return run_host_batch_streamed(*d, P, c, A, b, status, optF, optX, basis, stats);
+        return run_host_batch_pipelined(*d, P, c, A, b, status, optF, optX, basis, stats, chunks);
+    }
     return run_host_call(*d, P, c, A, n, b, nullptr, nullptr, nullptr, nullptr, status, optF, optX, basis, stats);
 }
 

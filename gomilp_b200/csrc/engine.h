@@ -30,6 +30,7 @@ struct Root {
 struct StreamEvents {
     cudaStream_t s = nullptr;
     cudaEvent_t e[6] = {};
+    int* h_counts = nullptr;  // 64 pinned ints: arrival counters of a streamed batch (run_host_batch_streamed)
     cudaError_t init();
     ~StreamEvents();
 };

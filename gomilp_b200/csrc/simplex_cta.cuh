@@ -76,6 +76,8 @@ struct BatchParams {
     double* work;           // HBM workspace for the tiers that need one: [gridDim][work_stride]
     long long work_stride;  // doubles per CTA
     int* queue;             // work-queue counter (zeroed before launch)
+    const int* ready;       // optional: number of LPs whose inputs have ARRIVED in HBM (written by the copy stream while
+                            // the kernel runs, see engine.cu run_host_batch_streamed); nullptr = everything is resident
     const int* lp_list;     // optional: work item k solves LP lp_list[k] (retry launches); nullptr = identity
     // ---- pivot trace (parity evidence): LP `trace_lp` records (phase, entering variable, leaving variable, bland)
     // for its first `trace_cap` pivots. Only the WARM-capable kernels carry the code (the bench kernel does not).
@@ -2827,11 +2829,20 @@ GM_DEV void cta_main(const BatchParams& P, double* wbase, double* bibase, double
         gm_sync();
     }
     for (;;) {
-        if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
+        if (gm_tid() == 0) {
+            int it = gm_atomic_add(P.queue, 1);
+            // streamed batches: the inputs of LP `it` may still be crossing PCIe; wait for the copy stream's counter
+            if (P.ready != nullptr && it < P.count && !gm_wait_ready(P.ready, it)) it = -1 - it;
+            *slot = it;
+        }
         gm_sync();
         const int item = *slot;
         gm_sync();
         if (item >= P.count) break;
+        if (item < 0) {  // the data never arrived (bounded wait): report, never hang
+            if (gm_tid() == 0) P.status[-1 - item] = GM_ERR_CUDA;
+            continue;
+        }
         const int lp = P.lp_list ? P.lp_list[item] : item;
         s.bind_lp(P, lp);
         s.solve(P, lp);
@@ -2869,11 +2880,19 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
         return;
     }
     for (;;) {
-        if (gm_tid() == 0) *slot = gm_atomic_add(P.queue, 1);
+        if (gm_tid() == 0) {
+            int it = gm_atomic_add(P.queue, 1);
+            if (P.ready != nullptr && it < P.count && !gm_wait_ready(P.ready, it)) it = -1 - it;
+            *slot = it;
+        }
         gm_sync();
         const int item = *slot;
         gm_sync();
         if (item >= P.count) break;
+        if (item < 0) {
+            if (gm_tid() == 0) P.status[-1 - item] = GM_ERR_CUDA;
+            continue;
+        }
         const int lp = P.lp_list ? P.lp_list[item] : item;
         s.bind_lp(P, lp);
         for (int k = 0; k < 8; ++k) s.prof_t[k] = 0;

@@ -57,7 +57,8 @@ typedef struct gm_options {
     int32_t force_tier;      /* 0 auto, else the gm_timing.tier to force (GM_ERR_TOO_LARGE if it does not fit) */
     int32_t reserved;        /* 1: tier 4 without the TMA staging ring (plain loads), for A/B measurements */
     int32_t coop_group;      /* tier 6: CTAs per LP. default min(SMs / LPs in the launch, m / 2) */
-    int32_t reserved2;
+    int32_t reserved2;       /* 1: large pinned host batches use one launch per slice instead of one launch gated on
+                                arrival counters (A/B measurements) */
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
 

@@ -91,7 +91,8 @@ typedef enum gm_bnb_mode { GM_BNB_COMPAT = 0, GM_BNB_FIXED = 1 } gm_bnb_mode;
 #define GM_BNB_WARM_START 4
 /* OR-ed into `mode`: checkSolution / feasibleForIP / branch run on the device (node_check + wave_scan kernels) so that
  * x never leaves the GPU, and the wave is sharded over the ranks of gm_comm_init when a communicator is set. Same
- * decisions, ids and node counts as the host replay (gm_milp_solve without the flag). Children are solved cold. */
+ * decisions, ids and node counts as the host replay (gm_milp_solve without the flag). GM_BNB_WARM_START is honoured
+ * on one GPU (the parents' inverses stay in that GPU's HBM); with a communicator children are solved cold. */
 #define GM_BNB_DEVICE_SCAN 8
 
 #ifdef __cplusplus

@@ -297,6 +297,15 @@ def test_device_scan_equals_host_replay_on_knapsack():
         assert logs_equal(a.log, d.log)
         if a.x is not None:
             assert np.array_equal(a.x, d.x) and a.z == d.z
+        # warm-started children: the device path keeps the parents' inverses in HBM exactly like gm_solve_wave_warm
+        aw = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                           mode=S.GM_BNB_FIXED | S.GM_BNB_WARM_START, heuristic=heur, node_limit=lim)
+        dw = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                           mode=S.GM_BNB_FIXED | S.GM_BNB_WARM_START | S.GM_BNB_DEVICE_SCAN, heuristic=heur, node_limit=lim)
+        assert (aw.status, aw.lp_status, aw.nodes, aw.waves, aw.pivots) == (dw.status, dw.lp_status, dw.nodes, dw.waves, dw.pivots)
+        assert logs_equal(aw.log, dw.log)
+        if a.status == S.GM_MILP_OK and aw.status == S.GM_MILP_OK:
+            assert abs(aw.z - a.z) <= RTOL * max(1.0, abs(a.z)) and aw.pivots < a.pivots
 
 
 def test_two_host_threads_on_one_device_do_not_interfere():

@@ -356,3 +356,29 @@ def test_results_are_bitwise_reproducible_run_to_run():
             assert np.array_equal(runs2[1]["x"], runs2[0]["x"])
     finally:
         gm.set_options()
+
+
+def test_streamed_pinned_batch_equals_the_sliced_and_the_plain_path():
+    """Large host batches: pinned inputs go through ONE launch whose CTAs wait on the copy stream's arrival counter
+    (run_host_batch_streamed); pageable inputs through one launch per slice. Same LPs, same kernel, same results."""
+    import torch
+    rng = np.random.default_rng(1234)
+    m, n, count = 64, 128, 2048
+    c, A, b = feasible_bounded_lp(rng, m, n, count)
+    plain = gm.simplex_batch(c, A, b)                       # pageable numpy memory: sliced launches
+    pc = torch.from_numpy(c).pin_memory().numpy()
+    pA = torch.from_numpy(A).pin_memory().numpy()
+    pb = torch.from_numpy(b).pin_memory().numpy()
+    streamed = gm.simplex_batch(pc, pA, pb)                 # pinned: one gated launch
+    tm = gm.last_timing()
+    assert tm["launches"] == 1 and tm["lps"] == count
+    try:
+        gm.set_options(no_streamed_batch=True)
+        sliced = gm.simplex_batch(pc, pA, pb)
+        assert gm.last_timing()["launches"] > 1
+    finally:
+        gm.set_options()
+    for other in (streamed, sliced):
+        assert np.array_equal(other["status"], plain["status"]) and (plain["status"] == S.GM_OK).all()
+        assert np.array_equal(other["optF"], plain["optF"]) and np.array_equal(other["x"], plain["x"])
+        assert np.array_equal(other["basis"], plain["basis"]) and np.array_equal(other["pivots"], plain["pivots"])
