@@ -349,11 +349,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     assert (status == 0).all(), "bench workload must solve to optimality"
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------------
-    hs = np.zeros(BATCH, dtype=np.int32)
-    hF = np.zeros(BATCH)
-    hx = np.zeros((BATCH, N))
-    hB = np.zeros((BATCH, M), dtype=np.int64)
-    hS = np.zeros((BATCH, 8), dtype=np.int32)
+    # results land in pinned host memory too (a device->host copy into pageable memory is staged and ~4x slower)
+    hs = torch.zeros(BATCH, dtype=torch.int32).pin_memory().numpy()
+    hF = torch.zeros(BATCH, dtype=torch.float64).pin_memory().numpy()
+    hx = torch.zeros(BATCH, N, dtype=torch.float64).pin_memory().numpy()
+    hB = torch.zeros(BATCH, M, dtype=torch.int64).pin_memory().numpy()
+    hS = torch.zeros(BATCH, 8, dtype=torch.int32).pin_memory().numpy()
     cn, An, bn = hc.numpy(), hA.numpy(), hb.numpy()
     import ctypes as C
     L = gm.capi.lib()

@@ -37,11 +37,19 @@ def _obj_stale(src: str, obj: str) -> bool:
 
 
 def _stale() -> bool:
+    """True when any object is older than its source / headers (an edit made WHILE a build was running leaves a
+    library that is newer than the source it lacks, so the library's own time says nothing) or the library is older
+    than an object."""
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    for src in SOURCES:
+        if not os.path.exists(os.path.join(CSRC, src)):
+            continue
+        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
+        if _obj_stale(src, obj) or os.path.getmtime(obj) > t:
+            return True
+    return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

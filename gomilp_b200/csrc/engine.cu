@@ -611,15 +611,16 @@ static int run_host_batch_streamed(DeviceCtx& d, gm::BatchParams P, const double
     t_timing = gm_timing{};
     int rc = launch_wave(d, P, ks, lk.se->e[1], lk.se->e[2], &t_timing);   // spins on `ready` until data arrives
     // slices of the batch, then the new arrival count, on the copy stream (pinned memory: truly asynchronous)
-    const int slices = (int)std::min<int64_t>(48, std::max<int64_t>(1, count / 128));
+    // c and b are small: they cross first, in one piece each; A follows in slices, each followed by the new count
+    const int slices = (int)std::min<int64_t>(24, std::max<int64_t>(1, count / 160));
     const int64_t per = (count + slices - 1) / slices;
     int* hc = lc.se->h_counts;
     CK(cudaEventRecord(lc.se->e[0], cs));
+    CK(cudaMemcpyAsync(dc.p, h_c, sizeof(double) * count * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(db.p, h_b, sizeof(double) * count * m, cudaMemcpyHostToDevice, cs));
     for (int k = 0; k < slices && rc == GM_OK; ++k) {
         const int64_t off = k * per, cnt = std::min<int64_t>(per, count - off);
         if (cnt <= 0) break;
-        CK(cudaMemcpyAsync(dc.as<double>() + off * n, h_c + off * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs));
-        CK(cudaMemcpyAsync(db.as<double>() + off * m, h_b + off * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(dA.as<double>() + off * m * n, h_A + off * m * n, sizeof(double) * cnt * m * n, cudaMemcpyHostToDevice, cs));
         hc[k] = (int)(off + cnt);
         CK(cudaMemcpyAsync(dready.p, &hc[k], sizeof(int), cudaMemcpyHostToDevice, cs));
