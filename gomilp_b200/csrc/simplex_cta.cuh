@@ -1164,7 +1164,9 @@ struct SolverT {
             for (;;) {
                 const int p = block_min_int(m - pfrom, [&](int q) { return mv[pfrom + q] <= GM_BLAND_ZERO_TOL ? pfrom + q : INT_MAX; });
                 if (p == INT_MAX) break;
-                if (swapped_cond(p, false) < GM_CONDITION_TOL) {
+                // same shortcut as the cooperative tier: a healthy pivot element cannot push cond_1 of the swapped basis
+                // anywhere near 1e16; the exact value is computed only for weak ones
+                if (fabs(al[p]) > 1e-6 * dmax || swapped_cond(p, false) < GM_CONDITION_TOL) {
                     l_out = p; e_out = i;
                     weak = !(fabs(al[p]) > 1e-9 * dmax);
                     return GM_OK;
@@ -2612,8 +2614,12 @@ struct SolverT {
                 const double amax = block_max(m, [&](int q) { return fabs(al[q]); });
                 const double ap = al[added];
                 // initializeFromBasic on the swapped basis (:594-600): LU.Solve fails iff the factor is exactly
-                // singular or cond_inf > 1e16 (lu.go:301,321); then the positivity test :459-468
-                if (!(swapped_cond(added, true) <= GM_CONDITION_TOL)) continue;
+                // singular or cond_inf > 1e16 (lu.go:301,321); then the positivity test :459-468. A column that does not
+                // reach the artificial's row at all (ap == 0: most of them) makes the swapped basis exactly singular; a
+                // healthy pivot element (> 1e-6 of the column) puts its condition number within ~1e12 of the current
+                // basis', far from 1e16; only in between is the exact condition number (O(m^2)) worth computing.
+                if (!(fabs(ap) > 0.0)) continue;
+                if (!(fabs(ap) > 1e-6 * fmax(1.0, amax)) && !(swapped_cond(added, true) <= GM_CONDITION_TOL)) continue;
                 weak = !(fabs(ap) > 1e-9 * fmax(1.0, amax));
                 const double theta = xb[added] / ap;
                 const int bad = block_min_int(m, [&](int i) {
