@@ -2604,9 +2604,34 @@ struct SolverT {
             gm_sync();
             for (int p = t; p < m; p += T) inb[basic[p]] = 1;
             gm_sync();
+            // One pass over A first: the pivot element of column v in the artificial's row is rho . a_v with rho = row
+            // `added` of the inverse. Columns where it is exactly zero (nearly all of them: they do not reach that row)
+            // give an exactly singular swapped basis, which the reference rejects one LU at a time (:589-605); marking
+            // them here (inb = 2) turns n trial solves of O(m^2) into one O(mn) sweep plus the few real candidates.
+            if constexpr (REG) reg_dump();
+            for (int j = t; j < m; j += T) t2[j] = Bi[(size_t)added * ldb + j];
+            gm_sync();
+            for (int v = t; v < n; v += T) {
+                if (inb[v]) continue;
+                double a0 = 0, a1 = 0;
+                int i = 0;
+                for (; i + 8 <= m; i += 8) {
+                    double w[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) w[u] = src_a(i + u, v);
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) { a0 += t2[i + u] * w[u]; a1 += t2[i + u + 1] * w[u + 1]; }
+                }
+                for (; i < m; ++i) a0 += t2[i] * src_a(i, v);
+                if (a0 + a1 == 0.0) inb[v] = 2;
+            }
+            gm_sync();
             bool done = false, weak = false;
             for (int v = 0; v < n && !done; ++v) {
-                if (inb[v]) continue;
+                if (inb[v]) {
+                    nrepair += inb[v] == 2;  // counted like the reference's trials
+                    continue;
+                }
                 nrepair++;
                 for (int i = t; i < m; i += T) t1[i] = src_a(i, v);
                 gm_sync();
