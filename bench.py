@@ -413,6 +413,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cpu_v, cpu_dt, _ = cpu_baseline(n_cpu, cores)
     h2d = BATCH * (M * N + M + N) * 8
     d2h = BATCH * (N + 1) * 8 + BATCH * 4 + BATCH * M * 8 + BATCH * 8 * 4
+    traffic, traffic_src = None, "null: no ncu capture of this round found under profiles/"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+            tr = json.load(f)["simplex_wave_reg"]
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        traffic_src = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this "
+                       "workload from the committed ncu --set full capture " + tr["source"])
+    except Exception:
+        pass
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -433,7 +442,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # bandwidth. `achieved` = SURVEY 8(d)'s algorithmic bytes per pivot x pivots per launch / launch time,
         # `peak` = the shared-memory bandwidth MEASURED in this run by gm_microbench_smem_gbs.
         "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
-                     "frac": achieved / smem_peak if smem_peak else None, "traffic": None,
+                     "frac": achieved / smem_peak if smem_peak else None, "traffic": traffic,
                      "kernel": "simplex_wave_reg", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_pivot": bytes_per_pivot(M, N),
                      "pivots_per_launch": pivots,
@@ -445,8 +454,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              else "fallback",
                              "note": "dram traffic of this kernel is the batch read once + results written once; "
                                      "ncu dram__bytes captures live under profiles/, not in this line"},
-                     "traffic_note": "null: not captured in this run (no ncu under bench.py); see profiles/ for the "
-                                     "ncu --set full capture of this command"},
+                     "traffic_source": traffic_src},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {n_cpu} LPs of rank 0's batch, {cores} threads, {cpu_dt:.1f} s"},
         "pivots_per_sec": pivots_all * args.steps / (total_ms * 1e-3),

@@ -38,6 +38,10 @@ GM_DEV int gm_block_id() { return (int)blockIdx.x; }
 GM_DEV void gm_threadfence() { __threadfence(); }
 GM_DEV void gm_spin_pause() {}
 GM_DEV long long gm_clock() { return clock64(); }
+// Hides where a value came from, so that the compiler keeps it instead of recomputing it from kernel parameters.
+template <class P>
+GM_DEV void gm_opaque(P*& p) { asm volatile("" : "+l"(p)); }
+GM_DEV void gm_opaque_i(int& v) { asm volatile("" : "+r"(v)); }
 // Waits until *ready > item (a counter the copy engine advances from another stream, hence system scope). Bounded:
 // ~10 s of polling, then false.
 GM_DEV bool gm_wait_ready(const int* ready, int item) {

@@ -577,10 +577,25 @@ struct SolverT {
             if (phase1)
                 for (int i = t; i < wrows; i += T) W[i * ldw + n] = i < m ? art[i] : 0.0;
         } else {
-            for_each_2d(wrows, ncols, [&](int i, int p) {
+            // thread = (column p, row group): the column's variable is looked up once, rows go eight at a time with the
+            // loads issued together (W and A may live in HBM: one latency per 8 rows instead of one per element)
+            int S = pow2ceil(ncols);
+            if (S > T) S = T;
+            const int RGn = T / S, col = t % S, rg = t / S;
+            for (int p = col; p < ncols; p += S) {
                 const int v = p < m ? basic[p] : nonbasic[p - m];
-                W[(size_t)i * ldw + p] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
-            });
+                for (int i0 = rg * 8; i0 < wrows; i0 += RGn * 8) {
+                    double w8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u;
+                        w8[u] = i >= m ? 0.0 : ((v == n) ? art[i] : src_a(i, v));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (i0 + u < wrows) W[(size_t)(i0 + u) * ldw + p] = w8[u];
+                }
+            }
         }
         for (int p = t; p < m; p += T) {
             const int v = basic[p];
@@ -2831,6 +2846,14 @@ struct SolverT {
         sel = inb;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
         refactor_period = P.refactor_period > 0 ? P.refactor_period : (P.hbm_layout && 2 * m > 100 ? 2 * m : 100);
+        if constexpr (REG) {
+            // Under the 128-register cap the compiler prefers to RE-DERIVE these pointers from the kernel parameters
+            // inside the pivot loop (ncu r02: 12 % of the stall samples on the lines above). Making the values opaque
+            // forces it to keep them (or spill them once, one LDL to reload) instead of recomputing the layout.
+            gm_opaque(W); gm_opaque(xb); gm_opaque(cb); gm_opaque(y); gm_opaque(al); gm_opaque(prow); gm_opaque(cn);
+            gm_opaque(r); gm_opaque(red); gm_opaque(basic); gm_opaque(nonbasic); gm_opaque(redi);
+            gm_opaque_i(m); gm_opaque_i(n); gm_opaque_i(ldw);
+        }
     }
     GM_DEV void bind_lp(const BatchParams& P, int lp) {
         c0 = P.c + (size_t)lp * P.c_stride;

@@ -21,13 +21,13 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "gomilp_b200/_bu
 dis = []
 for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
     out = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True).stdout
-    if kname in out:
+    if re.search(kname + r"E", out):   # the mangled name ends the identifier with E: not a prefix of another kernel
         dis = out.split("\n")
         break
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 raw_csv = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l][0]
+start = [i for i, l in enumerate(dis) if l.startswith(".text.") and re.search(kname + r"E", l)][0]
 pat = re.compile(r'//## File "([^"]+)", line (\d+)')
 chain_pat = re.compile(r'inlined at "([^"]+)", line (\d+)')
 cur, insts, i = None, [], start + 1

@@ -282,6 +282,9 @@ inline int gm_block_id() { return emu::current()->cur / emu::current()->T; }
 inline void gm_threadfence() {}
 inline void gm_spin_pause() { emu::yield_as(emu::RUN); }
 inline long long gm_clock() { return 0; }
+template <class P>
+inline void gm_opaque(P*&) {}
+inline void gm_opaque_i(int&) {}
 inline bool gm_wait_ready(const int* ready, int item) { return *ready > item; }
 inline void gm_atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 inline void gm_red_release_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
