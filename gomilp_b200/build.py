@@ -59,6 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    import time
+    t_start = time.time()  # objects are stamped with the START of the build: an edit made while it runs makes them stale
     # the two kernel translation units dominate (minutes of cicc each: the solver is one fully inlined function per
     # tier family), so every source is compiled to an object in its own nvcc process, in parallel, then linked
     procs, objs, logs = [], [], []
@@ -74,6 +76,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = pr.communicate()
         logs.append(" ".join(cmd) + "\n" + out)
         ok = ok and pr.returncode == 0
+        obj = cmd[cmd.index("-o") + 1]
+        if pr.returncode == 0 and os.path.exists(obj):
+            os.utime(obj, (t_start, t_start))
     if ok:
         cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-ldl"]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

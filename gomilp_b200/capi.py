@@ -35,7 +35,8 @@ class gm_timing(C.Structure):
 
 class gm_options(C.Structure):
     _fields_ = [("max_pivots", C.c_int32), ("refactor_period", C.c_int32), ("force_tier", C.c_int32),
-                ("reserved", C.c_int32), ("coop_group", C.c_int32), ("reserved2", C.c_int32)]
+                ("reserved", C.c_int32), ("coop_group", C.c_int32), ("reserved2", C.c_int32), ("robust", C.c_int32),
+                ("reserved3", C.c_int32)]
 
 
 class gm_milp_result(C.Structure):
@@ -50,7 +51,7 @@ WAVE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_dou
 EXPORTS = ["gm_device_count", "gm_init", "gm_shutdown", "gm_last_error", "gm_last_timing", "gm_set_options",
            "gm_simplex", "gm_simplex_batch", "gm_simplex_batch_device", "gm_upload_root", "gm_free_root",
            "gm_solve_wave", "gm_solve_wave_warm", "gm_milp_solve", "gm_trace_arm", "gm_trace_fetch",
-           "gm_milp_solve_device", "gm_microbench_smem_gbs", "gm_profile_arm", "gm_profile_fetch", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
+           "gm_milp_solve_device", "gm_thread_robust", "gm_microbench_smem_gbs", "gm_profile_arm", "gm_profile_fetch", "gm_comm_unique_id", "gm_comm_init", "gm_comm_destroy"]
 
 
 def lib():
@@ -78,6 +79,7 @@ def lib():
     L.gm_milp_solve.argtypes = [i64, vp, i64, vp, vp, i64, vp, vp, vp, i32, i32, i64, f64, vp,
                                 C.POINTER(gm_milp_result), DECISION_CB, WAVE_CB, vp]
     L.gm_milp_solve_device.argtypes = L.gm_milp_solve.argtypes
+    L.gm_thread_robust.argtypes = [C.c_int]
     L.gm_microbench_smem_gbs.argtypes = [C.POINTER(f64)]
     L.gm_comm_unique_id.argtypes = [vp]
     L.gm_comm_init.argtypes = [i32, i32, vp]
@@ -115,9 +117,9 @@ def init(device: int = 0):
 
 
 def set_options(max_pivots: int = 0, refactor_period: int = 0, force_tier: int = 0, no_tma_ring: bool = False,
-                coop_group: int = 0, no_streamed_batch: bool = False):
+                coop_group: int = 0, no_streamed_batch: bool = False, robust: bool = False):
     o = gm_options(max_pivots, refactor_period, force_tier, 1 if no_tma_ring else 0, coop_group,
-                   1 if no_streamed_batch else 0)
+                   1 if no_streamed_batch else 0, 1 if robust else 0, 0)
     _check(lib().gm_set_options(C.byref(o)))
 
 

@@ -448,6 +448,7 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
     const bool warm = (mode & GM_BNB_WARM_START) != 0;
     const double itol = warm ? 1e-9 : 0.0;
     const int bmode = mode & 3;
+    RobustScope robust_scope((mode & GM_BNB_ROBUST) != 0);
 
     // toInitialSubproblem (ilp.go:43-71) + convertToEqualities (subproblem.go:81-139): [A 0; G I]
     const int64_t m0 = meq + nineq, n0 = nvar + nineq;

@@ -124,6 +124,11 @@ extern "C" int gm_milp_solve(int64_t nvar, const double* c, int64_t meq, const d
 
     const bool warm = (mode & GM_BNB_WARM_START) != 0;
     const double itol = warm ? 1e-9 : 0.0;
+    struct RobustScope {  // GM_BNB_ROBUST: this thread's waves solve with gm_options.robust until we return
+        bool on;
+        explicit RobustScope(bool o) : on(o) { if (on) gm_thread_robust(+1); }
+        ~RobustScope() { if (on) gm_thread_robust(-1); }
+    } robust_scope((mode & GM_BNB_ROBUST) != 0);
     mode &= 3;
     Wave cur;
     cur.L = 0;

@@ -20,6 +20,7 @@ thread_local int t_device = -1;
 thread_local std::string t_err;
 thread_local gm_timing t_timing{};
 thread_local TraceReq t_trace;
+thread_local int t_robust = 0;
 
 int fail(cudaError_t e, const char* what) {
     t_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -139,6 +140,7 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
     }
     P.max_pivots = opt.max_pivots;
     P.refactor_period = opt.refactor_period;
+    P.robust = (opt.robust != 0 || t_robust > 0) ? 1 : 0;
     const gm::WsLayout wr = gm::ws_layout(m, n, kSmemThreads, true);
     const gm::WsLayout w1 = gm::ws_layout(m, n, kSmemThreads, false, false, true);   // tier 2
     const gm::WsLayout w3 = gm::ws_layout(m, n, kHbmThreads, false, true, true);    // tier 3
@@ -352,6 +354,12 @@ int gm_set_options(const gm_options* opt) {
     std::lock_guard<std::mutex> lk(g.mu);
     g.opt = *opt;
     return GM_OK;
+}
+
+int gm_thread_robust(int delta) {
+    t_robust += delta;
+    if (t_robust < 0) t_robust = 0;
+    return t_robust;
 }
 
 int gm_last_timing(gm_timing* out) {

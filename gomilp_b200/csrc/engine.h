@@ -59,7 +59,7 @@ struct Engine {
     std::mutex mu;
     DeviceCtx dev[kMaxDevices];
     int default_device = -1;
-    gm_options opt{0, 0, 0, 0, 0, 0};
+    gm_options opt{0, 0, 0, 0, 0, 0, 0, 0};
     std::map<gm_root_t, Root> roots;
     gm_root_t next_root = 1;
 };
@@ -83,6 +83,12 @@ extern thread_local int t_device;
 extern thread_local std::string t_err;
 extern thread_local gm_timing t_timing;
 extern thread_local TraceReq t_trace;
+extern thread_local int t_robust;  // > 0: waves launched by this thread solve with BatchParams::robust (GM_BNB_ROBUST)
+struct RobustScope {
+    explicit RobustScope(bool on) : on_(on) { if (on_) ++t_robust; }
+    ~RobustScope() { if (on_) --t_robust; }
+    bool on_;
+};
 
 int fail(cudaError_t e, const char* what);
 #define CK(call)                                              \

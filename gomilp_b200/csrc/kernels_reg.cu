@@ -36,7 +36,7 @@ cudaError_t reg_prepare(size_t smem, int* ctas_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, simplex_wave_reg, kSmemThreads, smem);
 }
 void reg_launch(const gm::BatchParams& P, int grid, size_t smem, cudaStream_t st) {
-    if (P.warm_parent || P.bi_out || P.trace) simplex_wave_reg_warm<<<grid, kSmemThreads, smem, st>>>(P);
+    if (P.warm_parent || P.bi_out || P.trace || P.robust) simplex_wave_reg_warm<<<grid, kSmemThreads, smem, st>>>(P);
     else simplex_wave_reg<<<grid, kSmemThreads, smem, st>>>(P);
 }
 }  // namespace gm_kernels

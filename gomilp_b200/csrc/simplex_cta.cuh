@@ -76,6 +76,8 @@ struct BatchParams {
     double* work;           // HBM workspace for the tiers that need one: [gridDim][work_stride]
     long long work_stride;  // doubles per CTA
     int* queue;             // work-queue counter (zeroed before launch)
+    int robust;             // non-reference: an LP on which the reference's rule set gives up (Bland dead end, numerically
+                            // singular basis after zero-step pivots, cycling) is re-solved on a slightly perturbed rhs
     const int* ready;       // optional: number of LPs whose inputs have ARRIVED in HBM (written by the copy stream while
                             // the kernel runs, see engine.cu run_host_batch_streamed); nullptr = everything is resident
     const int* lp_list;     // optional: work item k solves LP lp_list[k] (retry launches); nullptr = identity
@@ -2689,6 +2691,19 @@ struct SolverT {
         return GM_OK;
     }
 
+    // ---- robust mode (NOT the reference's behaviour; opt-in, gm_options.robust / GM_BNB_ROBUST) -----------------------
+    // On highly degenerate LPs (knapsack children: integer data, many active bound rows) the reference's rule set
+    // accepts zero-step Bland pivots on noise-level elements, reaches numerically singular bases (mat.Condition), dead
+    // ends (ErrBland) or cycles; GoMILP then panics (tree.go:272). With `robust` such an LP is solved once more on a
+    // right-hand side perturbed by ~1e-7 relative, which makes the vertices non-degenerate (every step is strictly
+    // positive, so the simplex method cannot cycle and never enters replaceBland); the optimal basis found is then
+    // re-evaluated on the TRUE right-hand side and, if that leaves it primal infeasible by a hair, repaired by
+    // Phase I / II from that basis. The answer is an optimal vertex of the original LP, confirmed by the usual polish.
+    // (Implemented as extra passes of the loop in solve(), so that the phases are not inlined a second time.)
+    GM_DEV static bool robust_retryable(int st) {
+        return st == GM_ERR_BLAND || st == GM_ERR_CONDITION || st == GM_ERR_ITERATION_LIMIT || st == GM_ERR_LINSOLVE ||
+               st == GM_PANIC_INITIAL_BASIC || (st > GM_ERR_PHASE1_WRAPPED && st < GM_ERR_BAD_SHAPE);
+    }
     // ---- one LP: simplex(), simplex.go:93-302 -------------------------------------------------------
     GM_DEV void solve(const BatchParams& P, int lp) {
         const int t = gm_tid(), T = gm_nthreads();
@@ -2759,14 +2774,48 @@ struct SolverT {
             } else {
                 if constexpr (WARM) warm = warm_start(P, lp);
             }
-            if (!have_start) status = find_initial_basic(fresh, warm);
-            if (status == GM_OK) {
-                status = main_loop(P.tol, 2, fresh);
-                ran_main = true;
+            // One pass normally. Robust mode (see above) may add two: (1) the same LP on a perturbed right-hand side,
+            // cold; (2) the true right-hand side again, started from the basis (1) ended on. The solver's phases appear
+            // once in the code, inside this loop.
+            int attempt = 0, cap0 = max_pivots;
+            for (;;) {
+                if (!have_start) status = find_initial_basic(fresh, warm);
+                if (status == GM_OK) {
+                    status = main_loop(P.tol, 2, fresh);
+                    ran_main = true;
+                }
+                bool again = false;
+                if constexpr (WARM) {
+                    if (P.robust && !P.initial_basic && !(attempt == 0 && warm)) {
+                        if (attempt == 0 && robust_retryable(status)) {
+                            scan_fb |= 2;  // reported in stats[5], bit 1
+                            max_pivots = piv1 + piv2 + 50 * (m + n) + 1000;
+                            for (int i = t; i < m; i += T) {
+                                const double bi = src_b(i);
+                                const double fr = (double)i * 0.6180339887498949;
+                                bv[i] = bi + 1e-7 * (1.0 + (fr - floor(fr))) * fmax(1.0, fabs(bi));
+                            }
+                            gm_sync();
+                            fresh = true; warm = false; ran_main = false;
+                            attempt = 1;
+                            again = true;
+                        } else if (attempt == 1) {
+                            for (int i = t; i < m; i += T) bv[i] = src_b(i);
+                            gm_sync();
+                            if (status == GM_OK) {  // re-evaluate the basis on the true right-hand side
+                                fresh = false; warm = true; ran_main = false;   // find_initial_basic(warm): from THIS basis
+                                attempt = 2;
+                                again = true;
+                            }
+                        }
+                    }
+                }
+                if (!again) break;
             }
+            if (attempt > 0) { max_pivots = cap0; warm = false; }
             // A warm start follows a different pivot path than the cold solve; if that path dies (ill-conditioned
             // basis, Bland dead end, iteration cap, unbounded ray at noise level) the engine re-solves the node from
-            // scratch in a follow-up launch (engine.cu: gm_solve_wave_warm).
+            // scratch in a follow-up launch (engine.cu: gm_solve_wave_warm, bnb_device.cu).
             if (warm && status != GM_OK && status != GM_ERR_INFEASIBLE) {
                 status = GM_ERR_WARM_RETRY;
                 ran_main = false;

@@ -49,6 +49,7 @@ GM_BRANCH_NAIVE = 2
 GM_BNB_COMPAT = 0
 GM_BNB_FIXED = 1
 GM_BNB_WARM_START = 4  # OR-ed into mode: children start from the parent's optimal basis (not a pivot-for-pivot replay)
+GM_BNB_ROBUST = 16  # OR-ed into mode: node LPs the reference's rules cannot finish are re-solved on a perturbed rhs
 GM_BNB_DEVICE_SCAN = 8  # OR-ed into mode: checkSolution / branch on the device, sharded over gm_comm_init's ranks
 
 STATUS_NAMES = {

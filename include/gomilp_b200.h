@@ -59,8 +59,17 @@ typedef struct gm_options {
     int32_t coop_group;      /* tier 6: CTAs per LP. default min(SMs / LPs in the launch, m / 2) */
     int32_t reserved2;       /* 1: large pinned host batches use one launch per slice instead of one launch gated on
                                 arrival counters (A/B measurements) */
+    int32_t robust;          /* 1: NOT the reference's behaviour. An LP on which the reference's rule set gives up
+                                (ErrBland, mat.Condition after zero-step pivots, the pivot cap where the reference would
+                                cycle) is solved once more on a right-hand side perturbed by ~1e-7 relative and the basis
+                                found re-evaluated on the true one; stats[5] bit 1 marks such LPs. Default 0: the failure
+                                is reported like the reference's error value. */
+    int32_t reserved3;
 } gm_options;
 int gm_set_options(const gm_options* opt); /* process-wide */
+/* Per-thread robust depth: while > 0, every wave the calling thread launches solves with gm_options.robust = 1
+ * whatever the process-wide options say (gm_milp_solve uses it for GM_BNB_ROBUST). Returns the new depth. */
+int gm_thread_robust(int delta);
 
 /* Cooperative tier (6) only: arm before a host-buffer compute call; every LP of that call reports 8 int64: SM clock
  * cycles its leader CTA spent in [0] the whole solve, [1] the cooperative main loop, [2] basis inversions, [3] polish

@@ -94,6 +94,10 @@ typedef enum gm_bnb_mode { GM_BNB_COMPAT = 0, GM_BNB_FIXED = 1 } gm_bnb_mode;
  * decisions, ids and node counts as the host replay (gm_milp_solve without the flag). GM_BNB_WARM_START is honoured
  * on one GPU (the parents' inverses stay in that GPU's HBM); with a communicator children are solved cold. */
 #define GM_BNB_DEVICE_SCAN 8
+/* OR-ed into `mode`: node LPs are solved with gm_options.robust = 1 (see gomilp_b200.h). The reference panics on the
+ * first relaxation its simplex cannot finish (tree.go:272); with this flag degenerate searches (0-1 knapsacks with
+ * bounds as rows) run through. No reference counterpart, like GM_BNB_FIXED. */
+#define GM_BNB_ROBUST 16
 
 #ifdef __cplusplus
 }

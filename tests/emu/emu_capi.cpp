@@ -7,6 +7,7 @@
 #include "../../gomilp_b200/csrc/simplex_cta.cuh"
 
 static const int* g_emu_lp_list = nullptr;
+static int g_emu_robust = 0;  // > 0: emulated launches solve with BatchParams::robust
 static int g_emu_coop_pan = 1;  // 0: force the inversion panel of the cooperative tier into (emulated) HBM
 static int g_emu_quad = 0;  // 1: run the generic solver as tier 2 (quad-mapped main loop)  // retry launches: work item k solves LP list[k]
 
@@ -53,6 +54,7 @@ int emu_simplex_batch_ex(int count, const double* c, const double* A, const doub
     P.basis = basis; P.stats = stats;
     P.warm_parent = warm_parent; P.warm_basis = warm_basis; P.warm_bi = warm_bi; P.bi_out = bi_out;
     P.lp_list = g_emu_lp_list;
+    P.robust = g_emu_robust > 0;
     int queue = 0;
     P.queue = &queue;
     if (reg && (T != 256 || m0 + L > 64)) return -2;
@@ -98,6 +100,7 @@ int emu_coop_batch(int count, const double* c, const double* A, const double* b,
     P.status = status; P.optF = optF; P.x = x; P.x_stride = x_stride; P.x_len = x_len;
     P.basis = basis; P.stats = stats;
     P.trace = trace; P.trace_cap = trace_cap; P.trace_lp = trace_lp;
+    P.robust = g_emu_robust > 0;
     int queue = 0;
     P.queue = &queue;
     P.hbm_layout = 1;
@@ -212,6 +215,8 @@ int gm_solve_wave_warm(gm_root_t root, int64_t nodes, int64_t L, const int32_t* 
     r.prev_m = (int)m;
     return rc == 0 ? GM_OK : GM_ERR_CUDA;
 }
+int gm_thread_robust(int delta) { g_emu_robust += delta; if (g_emu_robust < 0) g_emu_robust = 0; return g_emu_robust; }
+void emu_set_robust(int on) { g_emu_robust = on ? 1 : 0; }
 // the device-side scan (bnb_device.cu) is CUDA only: not available in the emulator build
 int gm_milp_solve_device(int64_t, const double*, int64_t, const double*, const double*, int64_t, const double*,
                          const double*, const uint8_t*, int32_t, int32_t, int64_t, double, double*, gm_milp_result*,

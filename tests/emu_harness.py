@@ -134,6 +134,10 @@ _DCB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
 _WCB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double)
 
 
+def set_robust(on: bool):
+    lib().emu_set_robust(C.c_int(int(on)))
+
+
 def milp_solve(c, A=None, b=None, G=None, h=None, integrality=None, heuristic=0, mode=0, node_limit=0,
                time_limit_s=0.0, T=64, reg=False, quad=False):
     """The product's gm_milp_solve (bnb_host.cpp) with every wave solved by the emulated kernel."""

@@ -373,3 +373,34 @@ def test_warm_started_waves_match_the_oracle_children():
         report(f"warm-started children, C5 n={n}: oracle optimum reproduced at 1e-9 on every node; {warm_piv} pivots "
                f"against {cold_piv} for the oracle's cold solves ({cold_piv / max(1, warm_piv):.1f}x fewer)")
         assert warm_piv < cold_piv
+
+
+@pytest.mark.timeout(900)
+def test_robust_mode_runs_through_degenerate_knapsack_searches():
+    """GM_BNB_ROBUST (no reference counterpart): 0-1 knapsacks with bounds as rows have children so degenerate that the
+    reference's own rule set gives up on them (the oracle panics at node 5 of the 120 x 40 instance with mat.Condition;
+    without the flag the engine reports the same failure class a few nodes later). With the flag those LPs are
+    re-solved on a perturbed right-hand side, the search runs through its budget, and what it finds is consistent with
+    HiGHS: every incumbent is feasible and no better than the true optimum; a search that finishes finds it."""
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    rng = np.random.default_rng(7)
+    for (n, m, lim) in ((60, 10, 6000), (120, 40, 300)):
+        p = knapsack(np.random.default_rng(7), n, m)
+        plain = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                              mode=S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN, heuristic=1, node_limit=lim, keep_log=False)
+        rob = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"],
+                            mode=S.GM_BNB_FIXED | S.GM_BNB_DEVICE_SCAN | S.GM_BNB_ROBUST, heuristic=1, node_limit=lim,
+                            keep_log=False)
+        hs = milp(p["c"], constraints=LinearConstraint(p["G"], -np.inf, p["h"]), integrality=p["integrality"],
+                  bounds=Bounds(0, np.inf), options={"time_limit": 60})
+        report(f"robust mode, knapsack {n}x{m}, budget {lim}: plain status {plain.status} (lp {plain.lp_status}) after "
+               f"{plain.nodes} nodes; robust status {rob.status} after {rob.nodes} nodes, incumbent "
+               f"{rob.z if rob.x is not None else None!r}; HiGHS optimum {hs.fun!r}")
+        assert plain.status == S.GM_MILP_PANIC_SOLVER_FAILURE           # the failure the flag is for
+        assert rob.status in (S.GM_MILP_OK, S.GM_MILP_DEADLINE_EXCEEDED) and rob.nodes > plain.nodes
+        if rob.x is not None:
+            x = rob.x[: len(p["c"])]
+            assert (p["G"] @ x <= p["h"] + 1e-6).all() and x.min() >= -1e-9
+            assert rob.z >= hs.fun - 1e-6 * max(1.0, abs(hs.fun))
+            if rob.status == S.GM_MILP_OK:
+                assert abs(rob.z - hs.fun) <= 1e-6 * max(1.0, abs(hs.fun))
