@@ -2781,7 +2781,9 @@ struct SolverT {
             for (;;) {
                 if (!have_start) status = find_initial_basic(fresh, warm);
                 if (status == GM_OK) {
-                    status = main_loop(P.tol, 2, fresh);
+                    // the robust passes stop at reduced costs that are noise against the costs (with the reference's
+                    // tol = 0 a value of -1e-17 is a pivot, and near-optimal bases can trade places for ever)
+                    status = main_loop(attempt > 0 ? fmax(P.tol, 1e-9 * fmax(1.0, cscale)) : P.tol, 2, fresh);
                     ran_main = true;
                 }
                 bool again = false;
@@ -2895,14 +2897,6 @@ struct SolverT {
         sel = inb;
         max_pivots = P.max_pivots > 0 ? P.max_pivots : 50 * (m + n) + 1000;
         refactor_period = P.refactor_period > 0 ? P.refactor_period : (P.hbm_layout && 2 * m > 100 ? 2 * m : 100);
-        if constexpr (REG) {
-            // Under the 128-register cap the compiler prefers to RE-DERIVE these pointers from the kernel parameters
-            // inside the pivot loop (ncu r02: 12 % of the stall samples on the lines above). Making the values opaque
-            // forces it to keep them (or spill them once, one LDL to reload) instead of recomputing the layout.
-            gm_opaque(W); gm_opaque(xb); gm_opaque(cb); gm_opaque(y); gm_opaque(al); gm_opaque(prow); gm_opaque(cn);
-            gm_opaque(r); gm_opaque(red); gm_opaque(basic); gm_opaque(nonbasic); gm_opaque(redi);
-            gm_opaque_i(m); gm_opaque_i(n); gm_opaque_i(ldw);
-        }
     }
     GM_DEV void bind_lp(const BatchParams& P, int lp) {
         c0 = P.c + (size_t)lp * P.c_stride;
