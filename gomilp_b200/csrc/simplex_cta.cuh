@@ -2287,6 +2287,7 @@ struct SolverT {
             if (t == 0) {
                 mail[0] = CMD_MAIN; mail[1] = tol; mail[2] = phase; mail[3] = fresh ? 1.0 : 0.0; mail[4] = since;
                 mail[5] = piv1; mail[6] = piv2; mail[7] = cscale; mail[8] = nn; mail[9] = ncols;
+                mail[11] = max_pivots;  // the leader may have raised it (robust passes)
             }
             long long t0 = gm_clock();
             grp_sync();
@@ -2539,6 +2540,7 @@ struct SolverT {
                 bool fresh = mail[3] != 0.0;
                 int since = (int)mail[4];
                 piv1 = (int)mail[5]; piv2 = (int)mail[6]; cscale = mail[7]; nn = (int)mail[8]; ncols = (int)mail[9];
+                max_pivots = (int)mail[11];
                 int e = 0;
                 coop_loop(tol, phase, fresh, since, e);
             } else if (cmd == CMD_INVERT) {
@@ -2694,9 +2696,10 @@ struct SolverT {
     // ---- robust mode (NOT the reference's behaviour; opt-in, gm_options.robust / GM_BNB_ROBUST) -----------------------
     // On highly degenerate LPs (knapsack children: integer data, many active bound rows) the reference's rule set
     // accepts zero-step Bland pivots on noise-level elements, reaches numerically singular bases (mat.Condition), dead
-    // ends (ErrBland) or cycles; GoMILP then panics (tree.go:272). With `robust` such an LP is solved once more on a
-    // right-hand side perturbed by ~1e-7 relative, which makes the vertices non-degenerate (every step is strictly
-    // positive, so the simplex method cannot cycle and never enters replaceBland); the optimal basis found is then
+    // ends (ErrBland) or cycles; GoMILP then panics (tree.go:272). With `robust` such an LP is solved once more with its
+    // Phase II on a right-hand side perturbed by ~1e-7 relative (B eps, i.e. every basic variable of the Phase-I vertex
+    // moved up), which makes the vertices non-degenerate (every step is strictly positive, so the simplex method
+    // cannot cycle and never enters replaceBland); the optimal basis found is then
     // re-evaluated on the TRUE right-hand side and, if that leaves it primal infeasible by a hair, repaired by
     // Phase I / II from that basis. The answer is an optimal vertex of the original LP, confirmed by the usual polish.
     // (Implemented as extra passes of the loop in solve(), so that the phases are not inlined a second time.)
@@ -2781,6 +2784,23 @@ struct SolverT {
             for (;;) {
                 if (!have_start) status = find_initial_basic(fresh, warm);
                 if (status == GM_OK) {
+                    if constexpr (WARM) {
+                        if (attempt == 1) {
+                            // Perturb the VERTEX, not b: every basic variable moves up by ~1e-7 relative (b moves by
+                            // B eps with it, so that refactorisations and the polish stay consistent). Phase I ran on
+                            // the true right-hand side: Gonum's construction pins the basics at 1, and a perturbed b
+                            // would put 1e-7-sized entries into the artificial column for the ratio test to pivot on.
+                            for (int i = t; i < m; i += T) {
+                                const double fr = (double)i * 0.6180339887498949;
+                                t1[i] = 1e-7 * (1.0 + (fr - floor(fr))) * fmax(1.0, fabs(xb[i]));
+                            }
+                            gm_sync();
+                            basis_mul(bv, bv, 1.0, t1);
+                            for (int i = t; i < m; i += T) xb[i] += t1[i];
+                            gm_sync();
+                            fresh = false;
+                        }
+                    }
                     // the robust passes stop at reduced costs that are noise against the costs (with the reference's
                     // tol = 0 a value of -1e-17 is a pivot, and near-optimal bases can trade places for ever)
                     status = main_loop(attempt > 0 ? fmax(P.tol, 1e-9 * fmax(1.0, cscale)) : P.tol, 2, fresh);
@@ -2792,12 +2812,6 @@ struct SolverT {
                         if (attempt == 0 && robust_retryable(status)) {
                             scan_fb |= 2;  // reported in stats[5], bit 1
                             max_pivots = piv1 + piv2 + 50 * (m + n) + 1000;
-                            for (int i = t; i < m; i += T) {
-                                const double bi = src_b(i);
-                                const double fr = (double)i * 0.6180339887498949;
-                                bv[i] = bi + 1e-7 * (1.0 + (fr - floor(fr))) * fmax(1.0, fabs(bi));
-                            }
-                            gm_sync();
                             fresh = true; warm = false; ran_main = false;
                             attempt = 1;
                             again = true;

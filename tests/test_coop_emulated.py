@@ -112,3 +112,23 @@ def test_forced_paths_fire_and_divergences_are_near_ties():
                         assert why != "REAL", (kind, k, d, why)
     print("paths fired (of 18 LPs):", fired, "divergences:", {w: why_all.count(w) for w in set(why_all)})
     assert fired["bland"] >= 4 and fired["repair"] >= 3 and fired["scan"] >= 6
+
+
+def test_robust_passes_reach_the_oracle_optimum():
+    """gm_options.robust (opt-in, no reference counterpart): an LP the first pass cannot finish is solved again with
+    its Phase II on a perturbed vertex and the basis found re-evaluated on the true right-hand side. Here the first
+    pass is cut short by a tiny pivot cap (a retryable status), on every kind of tier; the answer must be the oracle's."""
+    rng = np.random.default_rng(4)
+    c, A, b = feasible_bounded_lp(rng, 12, 30, 4)
+    o = oracle.simplex_batch(c, A, b)
+    E.set_robust(True)
+    try:
+        runs = [E.simplex_batch(c, A, b, max_pivots=5, T=64), E.simplex_batch(c, A, b, max_pivots=5, T=256, reg=True),
+                E.coop_batch(c, A, b, T=32, G=3, max_pivots=5)]
+    finally:
+        E.set_robust(False)
+    for g in runs:
+        assert (g["status"] == 0).all() and (g["stats"][:, 5] & 2).all()   # bit 1: the robust passes ran
+        assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
+    plain = E.simplex_batch(c, A, b, max_pivots=5, T=64)
+    assert (plain["status"] == 68).all()                                   # without the option: the cap is reported
