@@ -2781,6 +2781,12 @@ struct SolverT {
             // cold; (2) the true right-hand side again, started from the basis (1) ended on. The solver's phases appear
             // once in the code, inside this loop.
             int attempt = 0, cap0 = max_pivots;
+            double eps_rel = 1e-7;
+            if constexpr (WARM) {
+                // robust mode gives the reference's rule set a bounded try: a degenerate LP that has not finished after
+                // ~6 (m + n) pivots is stalling (healthy ones need 1 - 3 m), and the perturbed passes are cheaper
+                if (P.robust && !P.initial_basic && max_pivots > 6 * (m + n) + 1000) max_pivots = 6 * (m + n) + 1000;
+            }
             for (;;) {
                 if (!have_start) status = find_initial_basic(fresh, warm);
                 if (status == GM_OK) {
@@ -2792,7 +2798,7 @@ struct SolverT {
                             // would put 1e-7-sized entries into the artificial column for the ratio test to pivot on.
                             for (int i = t; i < m; i += T) {
                                 const double fr = (double)i * 0.6180339887498949;
-                                t1[i] = 1e-7 * (1.0 + (fr - floor(fr))) * fmax(1.0, fabs(xb[i]));
+                                t1[i] = eps_rel * (1.0 + (fr - floor(fr))) * fmax(1.0, fabs(xb[i]));
                             }
                             gm_sync();
                             basis_mul(bv, bv, 1.0, t1);
@@ -2824,11 +2830,19 @@ struct SolverT {
                                 again = true;
                             }
                         }
+                        if (!again && attempt >= 1 && robust_retryable(status) && eps_rel < 1e-4) {
+                            eps_rel *= 100.0;  // still stuck: once more from scratch with a coarser perturbation
+                            max_pivots = piv1 + piv2 + 50 * (m + n) + 1000;
+                            fresh = true; warm = false; ran_main = false;
+                            attempt = 1;
+                            again = true;
+                        }
                     }
                 }
                 if (!again) break;
             }
-            if (attempt > 0) { max_pivots = cap0; warm = false; }
+            max_pivots = cap0;
+            if (attempt > 0) warm = false;
             // A warm start follows a different pivot path than the cold solve; if that path dies (ill-conditioned
             // basis, Bland dead end, iteration cap, unbounded ray at noise level) the engine re-solves the node from
             // scratch in a follow-up launch (engine.cu: gm_solve_wave_warm, bnb_device.cu).

@@ -7,7 +7,9 @@ from gomilp_b200 import status as S
 from problems import knapsack, standard_form
 gm.init(0)
 p = knapsack(np.random.default_rng(7), 500, 200)
-r = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED, heuristic=1, node_limit=7)
+r = gm.milp_solve(p["c"], None, None, p["G"], p["h"], p["integrality"], mode=S.GM_BNB_FIXED | S.GM_BNB_ROBUST, heuristic=1,
+                  node_limit=int(sys.argv[1]) if len(sys.argv) > 1 else 7)
+print("replay:", r.status, r.lp_status, r.nodes, r.pivots)
 # rebuild the descriptors of the children of the logged nodes
 nodes = {0: []}
 order = []
@@ -24,11 +26,11 @@ root = gm.upload_root(c0, A0, b0)
 gm.set_options(max_pivots=12000)
 for nid in sorted(nodes):
     d = nodes[nid]
-    if len(d) != 3:
+    if nid < (int(sys.argv[2]) if len(sys.argv) > 2 else 7) or nid > (int(sys.argv[3]) if len(sys.argv) > 3 else 14):
         continue
     bvar = np.array([[t[0] for t in d]], np.int32); bs = np.array([[t[1] for t in d]]); br = np.array([[t[2] for t in d]])
-    for robust in (False, True):
-        gm.set_options(max_pivots=12000, robust=robust)
+    for robust in ((False, True) if len(sys.argv) <= 1 else (True,)):
+        gm.set_options(max_pivots=0 if robust else 12000, robust=robust)
         gm.trace_arm(0, 12000)
         t0 = time.perf_counter()
         w = gm.solve_wave(root, A0.shape[1], A0.shape[0], bvar, bs, br)
