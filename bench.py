@@ -182,10 +182,10 @@ def bnb_extra(gm):
         p3 = knapsack(np.random.default_rng(7), 500, 200)
         r3, dt3 = best_of(p3, 1 | 8, 7, reps=1)
         out["c3"] = {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, first 7 "
-                                 "nodes (3 waves), device-side scan, cold children; deeper nodes of this instance are "
-                                 "degenerate enough that the reference's own arithmetic aborts (mat.Condition, "
-                                 "tests/golden/c3_knapsack.npz), so the budget stops before them", **row(r3, dt3),
-                     "lp_status": r3.lp_status}
+                                 "nodes (3 waves), device-side scan, cold children, reference rule set only (deeper "
+                                 "nodes of this instance are degenerate enough that the reference's own arithmetic "
+                                 "aborts, tests/golden/c3_knapsack.npz; bnb_sharded.c3 runs deeper with GM_BNB_ROBUST)",
+                     **row(r3, dt3), "lp_status": r3.lp_status}
         from problems import c5_general_integer
         p5 = c5_general_integer(200)
         out["c5_n200"] = {"workload": "C5: general-integer MILP n=200 (300x500 + depth), FIXED most-infeasible, node budget "
@@ -244,10 +244,10 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
                                        "children, best of 2 after a warm-up run",
                            **timed(c5_general_integer(100), 1 | 8, 16383, 2)},
                "c3": {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, node "
-                                  "budget 255, device-side scan, FIFO blocks per rank, cold children, GM_BNB_ROBUST (the "
+                                  "budget 127, device-side scan, FIFO blocks per rank, cold children, GM_BNB_ROBUST (the "
                                   "reference's own rule set aborts on this instance's children beyond depth 2), best of 1 "
                                   "after a warm-up run",
-                      **timed(knapsack(np.random.default_rng(7), 500, 200), 1 | 8 | 16, 255, 1)}}
+                      **timed(knapsack(np.random.default_rng(7), 500, 200), 1 | 8 | 16, 127, 1)}}
         if world > 1:
             gm.capi.comm_destroy()
         return out
