@@ -240,9 +240,9 @@ def bnb_sharded_extra(gm, dist, dev, rank, world):
         out = {"gpus": world,
                "collective": "ncclAllGather of 32-byte node records, once per wave" if world > 1 else "none",
                "c5_n100": {"workload": "C5 general-integer MILP n=100 (150x250 + depth, bounds as rows), FIXED "
-                                       "most-infeasible, node budget 16383, device-side scan, FIFO blocks per rank, cold "
+                                       "most-infeasible, node budget 65535, device-side scan, FIFO blocks per rank, cold "
                                        "children, best of 2 after a warm-up run",
-                           **timed(c5_general_integer(100), 1 | 8, 16383, 2)},
+                           **timed(c5_general_integer(100), 1 | 8, 65535, 2)},
                "c3": {"workload": "C3: 0-1 knapsack n=500 m=200 seed 7 (700x1200 + depth), FIXED most-infeasible, node "
                                   "budget 127, device-side scan, FIFO blocks per rank, cold children, GM_BNB_ROBUST (the "
                                   "reference's own rule set aborts on this instance's children beyond depth 2), best of 1 "
