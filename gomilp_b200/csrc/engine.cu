@@ -210,6 +210,7 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
         P.hbm_layout = 1;
         P.coop_G = G;
         P.coop_pan = cl.pan_nb;
+        P.coop_small = cl.small_in_smem;
         if (t_trace.prof_armed && !t_trace.prof_in_flight) {  // leader clock cycles per activity (gm_profile_arm)
             CK(cudaMallocAsync(&t_trace.d_prof, sizeof(long long) * 8 * (size_t)P.count, stream));
             CK(cudaMemsetAsync(t_trace.d_prof, 0, sizeof(long long) * 8 * (size_t)P.count, stream));

@@ -88,6 +88,7 @@ struct BatchParams {
     // ---- cooperative tier (6): `coop_G` CTAs of one cooperative launch work on one LP (simplex_wave_coop) --------
     int coop_G;                     // CTAs per group
     int coop_pan;                   // inversion panel width when the panel fits in shared memory (16), else 0
+    int coop_small;                 // 1: groups of one CTA keep the solver's vectors in shared memory (see CoopLayout)
     unsigned long long* coop_bar;   // [groups] barrier counters, zeroed before launch
     long long* prof;                // optional [count][8]: leader clock cycles spent per activity (see coop_cta_main)
 };
@@ -177,6 +178,8 @@ struct CoopLayout {
     size_t Bi1, Tp, Rs, mail, group_doubles;              // HBM, relative to the group's slice
     size_t s_y, s_prow, s_ae, s_xb, s_al, s_f, s_r, s_part, s_red, s_bit, s_redi, smem_bytes;  // shared memory
     int pan_nb;  // 16: the inversion panel lives in shared memory (aliasing the main-loop scratch); 0: in HBM, 32 wide
+    size_t s_small;     // G == 1 only: the solver's vectors / index lists live in shared memory too (nobody else reads
+    int small_in_smem;  // them), which is what makes the leader's serial phases cheap on wide waves of mid-size LPs
 };
 #ifdef __CUDACC__
 __host__ __device__
@@ -211,6 +214,10 @@ inline CoopLayout coop_layout(int m, int n, int T, int G, size_t smem_limit = 20
     c.s_red = q; q += 2 * (size_t)T;    // two halves, used alternately by the block reductions
     c.s_bit = q; q += (mp + 1) / 2;     // ints
     c.s_redi = q; q += (2 * (size_t)T + 1) / 2;  // ints
+    q = (q + 1) & ~(size_t)1;
+    c.s_small = q;
+    c.small_in_smem = (G == 1 && (q * sizeof(double) + w.small_bytes + 1024 <= smem_limit)) ? 1 : 0;
+    if (c.small_in_smem) q += w.small_bytes / sizeof(double) + 2;
     c.smem_bytes = q * sizeof(double);
     return c;
 }
@@ -2984,7 +2991,9 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
     const WsLayout w = ws_layout(m, n, T, false, true);
     const CoopLayout c = coop_layout(m, n, T, G, P.coop_pan == 16 ? (size_t)1 << 30 : 0);
     double* base = P.work + (size_t)grp * P.work_stride;
-    s.bind_workspace(P, base + w.W, base + w.Bi, base + w.big_doubles, nullptr, nullptr);
+    // the host decided (BatchParams::coop_small) whether the vectors fit in shared memory beside the scratch
+    double* small = P.coop_small ? smem + c.s_small : base + w.big_doubles;
+    s.bind_workspace(P, base + w.W, base + w.Bi, small, nullptr, nullptr);
     s.G = G;
     s.rank = gm_block_id() % G;
     s.gbar = P.coop_bar + grp;

@@ -109,6 +109,7 @@ int emu_coop_batch(int count, const double* c, const double* A, const double* b,
     if (T % 32 != 0 || G < 1 || groups < 1) return -2;
     const gm::CoopLayout cl = gm::coop_layout(m0 + L, n0 + L, T, G, g_emu_coop_pan ? (size_t)200 * 1024 : 0);
     P.coop_pan = cl.pan_nb;
+    P.coop_small = cl.small_in_smem;
     std::vector<double> work((size_t)groups * cl.group_doubles + 16, 0.0);
     std::vector<unsigned long long> bars(groups, 0ull);
     P.work = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(work.data()) + 31) & ~uintptr_t(31));
