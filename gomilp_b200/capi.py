@@ -328,6 +328,6 @@ def profile_arm():
 
 
 def profile_fetch(lps: int = 1) -> np.ndarray:
-    out = np.zeros((lps, 8), dtype=np.int64)
+    out = np.zeros((lps, 16), dtype=np.int64)
     k = lib().gm_profile_fetch(_p(out), lps)
     return out[:k]

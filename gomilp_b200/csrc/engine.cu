@@ -212,8 +212,8 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
         P.coop_pan = cl.pan_nb;
         P.coop_small = cl.small_in_smem;
         if (t_trace.prof_armed && !t_trace.prof_in_flight) {  // leader clock cycles per activity (gm_profile_arm)
-            CK(cudaMallocAsync(&t_trace.d_prof, sizeof(long long) * 8 * (size_t)P.count, stream));
-            CK(cudaMemsetAsync(t_trace.d_prof, 0, sizeof(long long) * 8 * (size_t)P.count, stream));
+            CK(cudaMallocAsync(&t_trace.d_prof, sizeof(long long) * 16 * (size_t)P.count, stream));
+            CK(cudaMemsetAsync(t_trace.d_prof, 0, sizeof(long long) * 16 * (size_t)P.count, stream));
             P.prof = t_trace.d_prof;
             t_trace.prof_count = P.count;
             t_trace.prof_in_flight = true;
@@ -279,8 +279,8 @@ int launch_wave(DeviceCtx& d, gm::BatchParams P, cudaStream_t stream, cudaEvent_
 // Called by the host-buffer entry points once their stream has been synchronised: brings an armed trace back.
 void finish_trace() {
     if (t_trace.prof_in_flight) {
-        t_trace.prof.assign((size_t)t_trace.prof_count * 8, 0);
-        cudaMemcpyAsync(t_trace.prof.data(), t_trace.d_prof, sizeof(long long) * 8 * (size_t)t_trace.prof_count,
+        t_trace.prof.assign((size_t)t_trace.prof_count * 16, 0);
+        cudaMemcpyAsync(t_trace.prof.data(), t_trace.d_prof, sizeof(long long) * 16 * (size_t)t_trace.prof_count,
                         cudaMemcpyDeviceToHost, t_trace.prof_stream);
         cudaStreamSynchronize(t_trace.prof_stream);
         cudaFreeAsync(t_trace.d_prof, t_trace.prof_stream);
@@ -388,8 +388,8 @@ int gm_profile_arm(void) {
 
 int64_t gm_profile_fetch(int64_t* out, int64_t lps) {
     if (!out) return 0;
-    const int64_t k = std::min<int64_t>(lps, (int64_t)t_trace.prof.size() / 8);
-    std::memcpy(out, t_trace.prof.data(), sizeof(int64_t) * 8 * (size_t)k);
+    const int64_t k = std::min<int64_t>(lps, (int64_t)t_trace.prof.size() / 16);
+    std::memcpy(out, t_trace.prof.data(), sizeof(int64_t) * 16 * (size_t)k);
     return k;
 }
 

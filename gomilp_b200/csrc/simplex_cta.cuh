@@ -264,8 +264,10 @@ struct SolverT {
     double *s_y, *s_prow, *s_ae, *s_xb, *s_al, *s_f, *s_r, *s_part;  // shared-memory scratch of this CTA
     int* s_bit;
     double* s_pan;                // shared-memory inversion panel (aliases the scratch above), nullptr: use Tp
-    long long prof_t[8];          // leader: clock cycles in solve, main loop, inversion, polish, leader Bland, refactor;
-                                  // [6] main-loop calls, [7] polish calls
+    long long prof_t[16];         // leader: clock cycles in solve, main loop, inversion, polish, leader Bland, refactor;
+                                  // [6] main-loop calls, [7] polish calls; [8] input checks, [9] warm start, [10] initial
+                                  // basis / Phase-I set-up (outside its main loop), [11] repair loop, [12] results,
+                                  // [13] main-loop entry / exit (state load, buffer normalisation)
 
     GM_DEV void trace_pivot(int enter_var, int leave_var) {  // called by ONE thread, before the counters move
         if constexpr (WARM) {
@@ -1948,6 +1950,14 @@ struct SolverT {
     GM_DEV void prof_add(int k, long long t0) {
         if (gm_tid() == 0) prof_t[k] += gm_clock() - t0;
     }
+    // adds the time since t0 to category k and restarts the clock (cooperative kernel only: free elsewhere)
+    GM_DEV void pmark(int k, long long& t0) {
+        if constexpr (COOP) {
+            const long long now = gm_clock();
+            if (gm_tid() == 0) prof_t[k] += now - t0;
+            t0 = now;
+        }
+    }
 
     // Group barrier: every CTA of the group arrives, all earlier global writes of the group are visible afterwards.
     GM_DEV void grp_sync() {
@@ -2112,9 +2122,11 @@ struct SolverT {
         const int t = gm_tid(), T = gm_nthreads();
         const int r0 = (int)(((long long)rank * m) / G), r1 = (int)(((long long)(rank + 1) * m) / G), nr = r1 - r0;
         const int k0 = (int)(((long long)rank * nn) / G), k1 = (int)(((long long)(rank + 1) * nn) / G), tw = k1 - k0;
+        long long tp = gm_clock();
         for (int i = t; i < m; i += T) s_y[i] = y[i];
         for (int i = t; i < nr; i += T) { s_xb[i] = xb[r0 + i]; s_f[i] = 0.0; s_bit[i] = 0; s_al[i] = 0.0; }
         gm_sync();
+        pmark(13, tp);
         bool pending = false;
         int lprev = -1, skip = -1, reason;
         double skip_r = 0.0;
@@ -2269,6 +2281,7 @@ struct SolverT {
             if (++since >= refactor_period) { reason = CR_REFACTOR; break; }
         }
         // ---- hand the state back: finish a deferred update, gather every row in buffer 0, store xb / y
+        tp = gm_clock();
         if (pending) coop_rows_pass(r0, nr, true, lprev, false);
         {
             const int lane = t & 31, warp = t >> 5, nw = T >> 5;
@@ -2283,6 +2296,7 @@ struct SolverT {
         if (rank == 0)
             for (int j = t; j < m; j += T) y[j] = s_y[j];
         grp_sync();
+        pmark(13, tp);
         return reason;
     }
 
@@ -2564,6 +2578,8 @@ struct SolverT {
     GM_DEV int find_initial_basic(bool& fresh, bool warm) {
         const int t = gm_tid(), T = gm_nthreads();
         double cond1 = 0;
+        long long tp = 0;
+        if constexpr (COOP) tp = gm_clock();
         fresh = !warm;  // an inherited inverse is polished before it is trusted for an optimality verdict
         bool have = warm || try_permutation_basis();
         if (!have) {
@@ -2614,7 +2630,9 @@ struct SolverT {
             if (!xb_feasible()) return GM_PANIC_INITIAL_BASIC;
             fresh = true;
         }
+        pmark(10, tp);
         int rc = main_loop(GM_PHASE1_TOL, 1, fresh);
+        if constexpr (COOP) tp = gm_clock();
         if (rc != GM_OK) {
             if (rc == GM_ERR_ITERATION_LIMIT || rc == GM_PANIC_INITIAL_BASIC) return rc;
             return GM_ERR_PHASE1_WRAPPED + rc;  // :557-559
@@ -2695,8 +2713,10 @@ struct SolverT {
                 return GM_OK;
             }
         }
+        pmark(11, tp);
         build_w(n, false);  // Phase II lists: basis positions kept, non-basic ascending again (:174-197)
         bi_mul_t(y, cb);
+        pmark(10, tp);
         return GM_OK;
     }
 
@@ -2731,7 +2751,10 @@ struct SolverT {
             bv[i] = i < m ? src_b(i) : 0.0;
         }
         gm_sync();
+        long long tp = 0;
+        if constexpr (COOP) tp = gm_clock();
         status = verify_inputs();
+        pmark(8, tp);
         if (status != GM_OK) {
             optF = status == GM_ERR_UNBOUNDED ? -INFINITY : NAN;
         } else if (m > n) {
@@ -2783,6 +2806,7 @@ struct SolverT {
                 have_start = true;
             } else {
                 if constexpr (WARM) warm = warm_start(P, lp);
+                pmark(9, tp);
             }
             // One pass normally. Robust mode (see above) may add two: (1) the same LP on a perturbed right-hand side,
             // cold; (2) the true right-hand side again, started from the basis (1) ended on. The solver's phases appear
@@ -2871,6 +2895,7 @@ struct SolverT {
         }
 
         // ---- results ----
+        if constexpr (COOP) tp = gm_clock();
         double* xo = P.x + (size_t)lp * P.x_stride;
         for (int j = t; j < P.x_len; j += T) xo[j] = 0.0;
         gm_sync();
@@ -2908,6 +2933,7 @@ struct SolverT {
             }
         }
         gm_sync();
+        pmark(12, tp);
     }
 
     // ---- binding to the workspace (once per CTA: the shape is a launch constant) and to one LP ---------
@@ -3029,12 +3055,12 @@ GM_DEV void coop_cta_main(const BatchParams& P, double* smem, int* slot) {
         }
         const int lp = P.lp_list ? P.lp_list[item] : item;
         s.bind_lp(P, lp);
-        for (int k = 0; k < 8; ++k) s.prof_t[k] = 0;
+        for (int k = 0; k < 16; ++k) s.prof_t[k] = 0;
         const long long t0 = gm_clock();
         s.solve(P, lp);
         s.prof_add(0, t0);
         if (P.prof && gm_tid() == 0)
-            for (int k = 0; k < 8; ++k) P.prof[(size_t)lp * 8 + k] = s.prof_t[k];
+            for (int k = 0; k < 16; ++k) P.prof[(size_t)lp * 16 + k] = s.prof_t[k];
     }
     s.coop_post_exit();
 }

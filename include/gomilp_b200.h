@@ -71,12 +71,14 @@ int gm_set_options(const gm_options* opt); /* process-wide */
  * whatever the process-wide options say (gm_milp_solve uses it for GM_BNB_ROBUST). Returns the new depth. */
 int gm_thread_robust(int delta);
 
-/* Cooperative tier (6) only: arm before a host-buffer compute call; every LP of that call reports 8 int64: SM clock
+/* Cooperative tier (6) only: arm before a host-buffer compute call; every LP of that call reports 16 int64: SM clock
  * cycles its leader CTA spent in [0] the whole solve, [1] the cooperative main loop, [2] basis inversions, [3] polish
  * (refinement, may nest an inversion), [4] leader-only Bland pivots, [5] periodic refactorisation, and the counts
- * [6] main-loop entries, [7] polish calls. The per-wave device-timing extension of BnbMiddleware, one level down. */
+ * [6] main-loop entries, [7] polish calls; cycles in [8] the input checks, [9] the warm start, [10] initial basis / Phase-I
+ * set-up, [11] the Phase-I repair loop, [12] writing results, [13] main-loop entry / exit; [14..15] reserved.
+ * The per-wave device-timing extension of BnbMiddleware, one level down. */
 int gm_profile_arm(void);
-int64_t gm_profile_fetch(int64_t* out /* [lps][8] */, int64_t lps);
+int64_t gm_profile_fetch(int64_t* out /* [lps][16] */, int64_t lps);
 
 /* Measured shared-memory bandwidth of the current device in GB/s (all SMs streaming conflict-free 16-byte loads):
  * the denominator of the roofline of the shared-memory resident tiers (bench.py). */

@@ -18,13 +18,15 @@ for L in range(0, 11):
     w = gm.solve_wave(root, n0, m0, bv, bs, br, parent=par, warm=True)
     tm = gm.last_timing()
     pr = gm.profile_fetch(len(bv)).astype(float)
-    prm = pr.mean(axis=0) if len(pr) else np.zeros(8)
+    prm = pr.mean(axis=0) if len(pr) else np.zeros(16)
     s = w.stats
     print(json.dumps({"L": L, "nodes": len(bv), "tier": tm["tier"], "kernel_ms": tm["kernel_ms"], "launches": tm["launches"],
                       "piv_per_node": float((s[:, 0] + s[:, 1]).mean()), "p1_per_node": float(s[:, 0].mean()), "inv_per_node": float(s[:, 3].mean()),
                       "bland_per_node": float(s[:, 2].mean()), "repair_per_node": float(s[:, 6].mean()), "used_p1": float(s[:, 4].mean()),
                       "ok": int((w.status == 0).sum()), "leader_kcyc": {"solve": round(prm[0] / 1e3), "main": round(prm[1] / 1e3), "inv": round(prm[2] / 1e3),
-                      "polish": round(prm[3] / 1e3), "bland": round(prm[4] / 1e3), "entries": round(prm[6], 1), "polishes": round(prm[7], 1)}, "us_per_node_per_cta": 1e3 * tm["kernel_ms"] * min(148, len(bv)) / len(bv)}), flush=True)
+                      "polish": round(prm[3] / 1e3), "bland": round(prm[4] / 1e3), "entries": round(prm[6], 1), "polishes": round(prm[7], 1), "checks": round(prm[8] / 1e3),
+                      "warm_start": round(prm[9] / 1e3), "basis_setup": round(prm[10] / 1e3), "repair": round(prm[11] / 1e3), "results": round(prm[12] / 1e3),
+                      "loop_entry_exit": round(prm[13] / 1e3)}, "us_per_node_per_cta": 1e3 * tm["kernel_ms"] * min(148, len(bv)) / len(bv)}), flush=True)
     nb, ns, nr, npar = [], [], [], []
     for k in range(len(bv)):
         if w.status[k] != 0:
