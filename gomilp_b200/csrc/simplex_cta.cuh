@@ -2657,17 +2657,25 @@ struct SolverT {
             gm_sync();
             for (int v = t; v < n; v += T) {
                 if (inb[v]) continue;
-                double a0 = 0, a1 = 0;
+                double a0 = 0, a1 = 0, s0 = 0, s1 = 0;  // the dot product and the sum of |products| (its rounding scale)
                 int i = 0;
                 for (; i + 8 <= m; i += 8) {
                     double w[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) w[u] = src_a(i + u, v);
 #pragma unroll
-                    for (int u = 0; u < 8; u += 2) { a0 += t2[i + u] * w[u]; a1 += t2[i + u + 1] * w[u + 1]; }
+                    for (int u = 0; u < 8; u += 2) {
+                        const double p0 = t2[i + u] * w[u], p1 = t2[i + u + 1] * w[u + 1];
+                        a0 += p0; a1 += p1; s0 += fabs(p0); s1 += fabs(p1);
+                    }
                 }
-                for (; i < m; ++i) a0 += t2[i] * src_a(i, v);
-                if (a0 + a1 == 0.0) inb[v] = 2;
+                for (; i < m; ++i) {
+                    const double p0 = t2[i] * src_a(i, v);
+                    a0 += p0; s0 += fabs(p0);
+                }
+                // zero, or pure cancellation noise (an inherited product-form inverse has 1e-17s where a fresh LU has
+                // exact zeros): the swapped basis is singular to working precision, cond >= 1e16, rejected either way
+                if (fabs(a0 + a1) <= 1e-12 * (s0 + s1)) inb[v] = 2;
             }
             gm_sync();
             bool done = false, weak = false;
