@@ -2698,7 +2698,11 @@ struct SolverT {
                 if (!(fabs(ap) > 0.0)) continue;
                 if (!(fabs(ap) > 1e-6 * fmax(1.0, amax)) && !(swapped_cond(added, true) <= GM_CONDITION_TOL)) continue;
                 weak = !(fabs(ap) > 1e-9 * fmax(1.0, amax));
-                const double theta = xb[added] / ap;
+                // The artificial sits at level |x| <= 1e-12 = zero by the reference's own test (:563), so the swap does
+                // not move the vertex: the reference's fresh solve of the swapped basis returns the same xb (its zeros
+                // stay within 1e-16 of zero). Dividing the artificial's rounding noise by the pivot element instead
+                // would smear it over the degenerate basics and reject candidate after candidate.
+                const double theta = 0.0;
                 const int bad = block_min_int(m, [&](int i) {
                     const double nx = (i == added) ? theta : xb[i] - al[i] * theta;
                     return nx < -GM_INIT_POS_TOL ? i : INT_MAX;
