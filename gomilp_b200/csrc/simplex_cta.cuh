@@ -2695,7 +2695,8 @@ struct SolverT {
                 // reach the artificial's row at all (ap == 0: most of them) makes the swapped basis exactly singular; a
                 // healthy pivot element (> 1e-6 of the column) puts its condition number within ~1e12 of the current
                 // basis', far from 1e16; only in between is the exact condition number (O(m^2)) worth computing.
-                if (!(fabs(ap) > 0.0)) continue;
+                // ... and below 1e-14 of the column it is rounding noise of an exact zero (cond >= 1e14 cond(B)).
+                if (!(fabs(ap) > 1e-14 * fmax(1.0, amax))) continue;
                 if (!(fabs(ap) > 1e-6 * fmax(1.0, amax)) && !(swapped_cond(added, true) <= GM_CONDITION_TOL)) continue;
                 weak = !(fabs(ap) > 1e-9 * fmax(1.0, amax));
                 // The artificial sits at level |x| <= 1e-12 = zero by the reference's own test (:563), so the swap does
