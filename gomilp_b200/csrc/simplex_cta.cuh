@@ -2034,6 +2034,66 @@ struct SolverT {
         int clen = (m + C - 1) / C;
         clen = (clen + 31) & ~31;
         const int npairs = nr * C;
+        if (C == 1 && m <= 256) {
+            // Short rows, several rows per warp (a wide wave of mid-size LPs, one CTA each): a row is only 1 - 4 loads
+            // per lane, so walking the rows one after the other costs one L2 latency per row. Four rows go together:
+            // all their loads are issued before the first update, then the four dot products are reduced.
+            for (int base = warp; base < nr; base += 4 * nw) {
+                double2 v[4][4];
+                double fr[4], acc[4];
+                bool isl[4], wrr[4], ok[4];
+                double* dstr[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ri = base + q * nw;
+                    ok[q] = ri < nr;
+                    const int rr = ok[q] ? ri : base;
+                    const int i = r0 + rr;
+                    const int bit = s_bit[rr];
+                    fr[q] = s_f[rr];
+                    isl[q] = pending && i == lprev;
+                    wrr[q] = ok[q] && pending && (isl[q] || fr[q] != 0.0);
+                    const double* src = bi_buf(bit) + (size_t)i * ldb;
+                    dstr[q] = bi_buf(bit ^ 1) + (size_t)i * ldb;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = 2 * lane + 64 * k;
+                        v[q][k] = (ok[q] && j < m) ? *reinterpret_cast<const double2*>(src + j) : double2{0.0, 0.0};
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    double a0 = 0, a1 = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = 2 * lane + 64 * k;
+                        if (j < m) {
+                            const bool two = j + 1 < m;  // the row may end on an odd column
+                            if (wrr[q]) {
+                                const double p0 = s_prow[j], p1 = two ? s_prow[j + 1] : 0.0;
+                                v[q][k].x = isl[q] ? p0 : v[q][k].x - fr[q] * p0;
+                                v[q][k].y = isl[q] ? p1 : v[q][k].y - fr[q] * p1;
+                                if (two) *reinterpret_cast<double2*>(dstr[q] + j) = v[q][k];
+                                else dstr[q][j] = v[q][k].x;
+                            }
+                            if (with_dot) {
+                                a0 += v[q][k].x * s_ae[j];
+                                if (two) a1 += v[q][k].y * s_ae[j + 1];
+                            }
+                        }
+                    }
+                    acc[q] = a0 + a1;
+                }
+                if (with_dot) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        double a = acc[q];
+                        for (int d = 16; d >= 1; d >>= 1) a += gm_shfl_xor(a, d);
+                        if (lane == 0 && ok[q]) s_part[base + q * nw] = a;
+                    }
+                }
+            }
+        } else
         for (int pr = warp; pr < npairs; pr += nw) {
             const int ri = pr / C, ch = pr % C;
             const int i = r0 + ri;
