@@ -14,7 +14,7 @@ import gomilp_b200 as gm
 import oracle
 from gomilp_b200 import status as S
 from parity_tools import classify_divergence, compare_bnb_logs, first_divergence
-from problems import c5_general_integer, feasible_bounded_lp, knapsack, node_lp, standard_form
+from problems import c5_general_integer, feasible_bounded_lp, knapsack, node_lp, raw_lp, standard_form
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -407,3 +407,58 @@ def test_robust_mode_runs_through_degenerate_knapsack_searches():
             assert rob.z >= hs.fun - 1e-6 * max(1.0, abs(hs.fun))
             if rob.status == S.GM_MILP_OK:
                 assert abs(rob.z - hs.fun) <= 1e-6 * max(1.0, abs(hs.fun))
+
+
+@pytest.mark.timeout(900)
+def test_cooperative_tier_agrees_with_the_single_cta_tiers_on_random_shapes():
+    """Cross-tier consistency on shapes nobody tuned for: odd m, n barely above m, groups that do not divide the rows,
+    waves with branch rows, raw (infeasible / unbounded) data. Tier 6 with several group sizes must return what the
+    one-CTA-per-LP tiers return: same status, z and x at 1e-9."""
+    rng = np.random.default_rng(2026)
+    checked = 0
+    for trial in range(10):
+        m = int(rng.integers(65, 260))
+        n = int(rng.integers(m + 1, int(2.4 * m) + 2))
+        count = int(rng.choice([1, 3, 7]))
+        if trial % 3 == 2:
+            c, A, b = raw_lp(rng, m, n, count, 0.2)
+        else:
+            c, A, b = feasible_bounded_lp(rng, m, n, count)
+        try:
+            gm.set_options(force_tier=5)
+            ref = gm.simplex_batch(c, A, b)
+            for G in (1, 2, 5, 37):
+                gm.set_options(force_tier=6, coop_group=G)
+                got = gm.simplex_batch(c, A, b)
+                assert gm.last_timing()["tier"] == 6
+                assert np.array_equal(got["status"], ref["status"]), (m, n, count, G, got["status"], ref["status"])
+                ok = ref["status"] == S.GM_OK
+                if ok.any():
+                    assert rel(got["optF"][ok], ref["optF"][ok]) <= RTOL and rel(got["x"][ok], ref["x"][ok]) <= 1e-8
+                checked += int(ok.sum())
+        finally:
+            gm.set_options()
+    # waves over a shared root with branch rows (the B&B path), several group sizes
+    p = c5_general_integer(60)
+    c0, A0, b0 = standard_form(p)
+    m0, n0 = A0.shape
+    nodes, L = 5, 4
+    bvar = rng.integers(0, 60, size=(nodes, L)).astype(np.int32)
+    bsign = rng.choice([-1.0, 1.0], size=(nodes, L))
+    brhs = np.where(bsign > 0, rng.integers(2, 8, size=(nodes, L)), -rng.integers(1, 4, size=(nodes, L))).astype(float)
+    root = gm.upload_root(c0, A0, b0)
+    try:
+        gm.set_options(force_tier=2)
+        ref = gm.solve_wave(root, n0, m0, bvar, bsign, brhs)
+        for G in (1, 3, 20):
+            gm.set_options(force_tier=6, coop_group=G)
+            got = gm.solve_wave(root, n0, m0, bvar, bsign, brhs)
+            assert np.array_equal(got.status, ref.status)
+            ok = ref.status == S.GM_OK
+            if ok.any():
+                assert rel(got.z[ok], ref.z[ok]) <= RTOL and rel(got.x[ok], ref.x[ok]) <= 1e-8
+    finally:
+        gm.set_options()
+        gm.free_root(root)
+    report(f"cross-tier consistency: tier 6 with 1 / 2 / 5 / 37 CTAs per LP against tier 5 on 10 random shapes "
+           f"(m 65..260, {checked} optimal LPs compared at 1e-9) and against tier 2 on a 5-node wave with 4 branch rows")
