@@ -4,7 +4,7 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
 import gomilp_b200 as gm
 gm.init(0)
-z = np.load("tests/golden/degenerate_105x137.npz"); c, A, b = z["c"][3:4], z["A"][3:4], z["b"][3:4]
+z = np.load("tests/golden/degenerate_105x137.npz"); c, A, b = z["c"], z["A"], z["b"]
 for (tier, G, robust) in ((5, 0, False), (3, 0, False), (6, 1, False), (6, 2, False), (6, 5, False), (6, 37, False), (6, 1, True), (5, 0, True)):
     gm.set_options(force_tier=tier, coop_group=G, robust=robust)
     g = gm.simplex_batch(c, A, b)

@@ -132,3 +132,16 @@ def test_robust_passes_reach_the_oracle_optimum():
         assert _close(g["optF"], o["optF"]) and _close(g["x"], o["x"])
     plain = E.simplex_batch(c, A, b, max_pivots=5, T=64)
     assert (plain["status"] == 68).all()                                   # without the option: the cap is reported
+
+
+def test_degenerate_lp_that_stalls_some_gpu_schedules():
+    """tests/golden/degenerate_105x137.npz: the LP (n barely above m, a degenerate optimal vertex) on which tier 6 with
+    1 - 5 CTAs stalls at the optimal vertex on the GPU while tiers 3 / 5 and 37 CTAs do not. The oracle
+    and the emulated cooperative tier both get through it on Bland calls; they must agree on the optimum."""
+    z = np.load(os.path.join(HERE, "golden", "degenerate_105x137.npz"))
+    c, A, b = z["c"], z["A"], z["b"]
+    o = oracle.simplex(c[0], A[0], b[0])
+    assert o.status == 0 and o.bland_calls > 50
+    g = E.coop_batch(c, A, b, T=64, G=2)
+    assert g["status"][0] == 0 and g["stats"][0, 2] > 50
+    assert _close(g["optF"][0], o.optF) and _close(g["x"][0], o.x)
