@@ -380,6 +380,28 @@ struct Buf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// Every device buffer of one search. Lives with the leased stream (StreamEvents::arena) and is reused by the next
+// search on that stream: the waves double in width, so a fresh set of buffers means ~15 growing allocations per
+// buffer and, with warm start, GBs of stream-ordered allocation per call.
+struct BnbArena {
+    Buf d_integ, d_rec, d_dec, d_sum, d_incx;
+    Buf desc_v[2], desc_s[2], desc_r[2], par[2], ids[2];
+    Buf d_status, d_z, d_x, d_stats;
+    Buf wbi[2], wbasis[2], d_retry, d_nretry;
+    WaveSummary* h_sum = nullptr;  // pinned
+    int* h_nretry = nullptr;       // pinned
+    explicit BnbArena(cudaStream_t st)
+        : d_integ(st), d_rec(st), d_dec(st), d_sum(st), d_incx(st), desc_v{Buf(st), Buf(st)}, desc_s{Buf(st), Buf(st)},
+          desc_r{Buf(st), Buf(st)}, par{Buf(st), Buf(st)}, ids{Buf(st), Buf(st)}, d_status(st), d_z(st), d_x(st),
+          d_stats(st), wbi{Buf(st), Buf(st)}, wbasis{Buf(st), Buf(st)}, d_retry(st), d_nretry(st) {}
+    ~BnbArena() {
+        if (h_sum) cudaFreeHost(h_sum);
+        if (h_nretry) cudaFreeHost(h_nretry);
+    }
+    BnbArena(const BnbArena&) = delete;
+    BnbArena& operator=(const BnbArena&) = delete;
+};
+
 }  // namespace
 
 namespace gm_engine {
@@ -483,15 +505,21 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
     cudaStream_t st = se.s;
     int engine_rc = GM_OK;
     {
-        Buf d_integ(st), d_rec(st), d_dec(st), d_sum(st), d_incx(st);
-        Buf desc_v[2] = {Buf(st), Buf(st)}, desc_s[2] = {Buf(st), Buf(st)}, desc_r[2] = {Buf(st), Buf(st)};
-        Buf par[2] = {Buf(st), Buf(st)}, ids[2] = {Buf(st), Buf(st)};
-        Buf d_status(st), d_z(st), d_x(st), d_stats(st);
+        if (se.arena == nullptr) {
+            se.arena = new BnbArena(st);
+            se.arena_free = [](void* a) { delete static_cast<BnbArena*>(a); };
+        }
+        BnbArena& ar = *static_cast<BnbArena*>(se.arena);
+        Buf &d_integ = ar.d_integ, &d_rec = ar.d_rec, &d_dec = ar.d_dec, &d_sum = ar.d_sum, &d_incx = ar.d_incx;
+        Buf (&desc_v)[2] = ar.desc_v, (&desc_s)[2] = ar.desc_s, (&desc_r)[2] = ar.desc_r;
+        Buf (&par)[2] = ar.par, (&ids)[2] = ar.ids;
+        Buf &d_status = ar.d_status, &d_z = ar.d_z, &d_x = ar.d_x, &d_stats = ar.d_stats;
         // warm start (GM_BNB_WARM_START, one GPU): every node's final basis and inverse stay in HBM for its children
-        Buf wbi[2] = {Buf(st), Buf(st)}, wbasis[2] = {Buf(st), Buf(st)}, d_retry(st), d_nretry(st);
-        int* h_nretry = nullptr;
+        Buf (&wbi)[2] = ar.wbi, (&wbasis)[2] = ar.wbasis;
+        Buf &d_retry = ar.d_retry, &d_nretry = ar.d_nretry;
+        int*& h_nretry = ar.h_nretry;
         bool prev_kept = false;
-        WaveSummary* h_sum = nullptr;
+        WaveSummary*& h_sum = ar.h_sum;
         std::vector<NodeRec> h_rec;
         std::vector<int> h_dec, h_par;
         std::vector<long long> h_ids, h_pids;
@@ -514,8 +542,8 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
         int L = 0, cur = 0;
         std::vector<long long> prev_ids;  // ids of the previous wave (parents), kept only for the decision callback
 
-        CKE(cudaMallocHost(&h_sum, sizeof(WaveSummary)));
-        CKE(cudaMallocHost(&h_nretry, sizeof(int)));
+        if (h_sum == nullptr) CKE(cudaMallocHost(&h_sum, sizeof(WaveSummary)));
+        if (h_nretry == nullptr) CKE(cudaMallocHost(&h_nretry, sizeof(int)));
         CKE(d_nretry.reserve(sizeof(int)));
         CKE(d_integ.reserve(n0));
         CKE(cudaMemcpyAsync(d_integ.p, integ.data(), n0, cudaMemcpyHostToDevice, st));
@@ -692,9 +720,7 @@ int gm_milp_solve_device(int64_t nvar, const double* c, int64_t meq, const doubl
             result->status = timed_out ? GM_MILP_DEADLINE_EXCEEDED : GM_MILP_OK;
         }
     done:
-        cudaStreamSynchronize(st);
-        if (h_sum) cudaFreeHost(h_sum);
-        if (h_nretry) cudaFreeHost(h_nretry);
+        cudaStreamSynchronize(st);  // the arena (device buffers, pinned summaries) stays with the stream
 #undef CKE
 #undef NKE
     }

@@ -34,6 +34,7 @@ cudaError_t StreamEvents::init() {
     return r;
 }
 StreamEvents::~StreamEvents() {
+    if (arena && arena_free) arena_free(arena);  // frees on `s`: before the stream goes
     if (h_counts) cudaFreeHost(h_counts);
     for (auto& ev : e)
         if (ev) cudaEventDestroy(ev);

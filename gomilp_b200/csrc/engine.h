@@ -31,6 +31,10 @@ struct StreamEvents {
     cudaStream_t s = nullptr;
     cudaEvent_t e[6] = {};
     int* h_counts = nullptr;  // 64 pinned ints: arrival counters of a streamed batch (run_host_batch_streamed)
+    // scratch of the device-side B&B scheduler (bnb_device.cu), kept with the stream across calls: wave buffers only
+    // grow, so a second search of a similar size allocates nothing (stream-ordered allocation of GBs is not free)
+    void* arena = nullptr;
+    void (*arena_free)(void*) = nullptr;
     cudaError_t init();
     ~StreamEvents();
 };
