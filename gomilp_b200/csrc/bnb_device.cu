@@ -369,6 +369,9 @@ struct Buf {
     size_t cap = 0;
     cudaStream_t s;
     explicit Buf(cudaStream_t s_) : s(s_) {}
+    Buf(Buf&& o) noexcept : p(o.p), cap(o.cap), s(o.s) { o.p = nullptr; o.cap = 0; }  // owning: moves only
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
     ~Buf() { if (p) cudaFreeAsync(p, s); }
     cudaError_t reserve(size_t bytes) {  // contents are NOT preserved
         if (bytes <= cap) return cudaSuccess;
